@@ -1,0 +1,36 @@
+"""B200-native (sm_100a) region-proposal / RoI hot path of antoineBarbez/2D_object_detection.
+
+The sub-packages mirror the reference's module paths so the path drops into ``faster_rcnn.py`` /
+``train_faster_rcnn.py``:
+
+    utils.boxes            clip_to_window, decode, encode, to_absolute, to_relative
+    utils.metrics          area, intersection, iou
+    utils.post_processing  postprocess_output  (+ stage functions decode_filter, non_max_suppression)
+    utils.training         generate_targets, generate_targets_batched, get_sample_indices
+    models.detectors.rpn_detector        generate_anchors, valid_anchor_indices, RPNAnchors
+    models.detectors.fast_rcnn_detector  ROIPooling (differentiable)
+    pipeline               ProposalRoIPipeline (host buffers in, host buffers out)
+
+Python only marshals arguments; all arithmetic runs in hand-written CUDA kernels behind the C ABI of
+``include/frcnn_b200.h`` (``libfrcnn_b200.so``).  There is no CPU, PyTorch-eager or Triton fallback: importing
+this package without the built library raises.
+
+The directory name starts with a digit, so import it with
+``importlib.import_module("2d_object_detection_b200")`` or through the ``b200det`` alias module.
+"""
+from . import _lib
+
+_lib.load()  # fail loudly at import if the CUDA library has not been built
+
+from . import synthetic  # noqa: E402
+from .models.detectors.fast_rcnn_detector import ROIPooling, roi_pool_backward, roi_pool_forward  # noqa: E402
+from .models.detectors.rpn_detector import (RPNAnchors, generate_anchors,  # noqa: E402
+                                            remove_invalid_anchors_and_predictions, valid_anchor_indices)
+from .pipeline import ProposalRoIPipeline  # noqa: E402
+from .utils.boxes import clip_to_window, decode, encode, to_absolute, to_relative  # noqa: E402
+from .utils.metrics import area, intersection, iou  # noqa: E402
+from .utils.post_processing import decode_filter, non_max_suppression, postprocess_output  # noqa: E402
+from .utils.training import (generate_targets, generate_targets_batched, get_sample_indices,  # noqa: E402
+                             rpn_objectness_labels)
+
+__version__ = "0.1.0"

@@ -1,0 +1,620 @@
+// Proposal selection: utils/post_processing.py:6-63 postprocess_output, i.e. decode -> to_relative ->
+// drop background column -> tf.image.combined_non_max_suppression -> padded outputs.
+//
+// Three kernels, one launch each for the whole batch:
+//   decode_filter_kernel  fused decode + normalise + score threshold, one float4 per box, 44 B/box.
+//   nms_select_kernel     one persistent CTA per (image, class) segment.  It walks the candidates in
+//                         (score desc, index asc) order in chunks of 512: an 11-bit radix *select* finds
+//                         the next chunk (no full sort of N), a bitonic network orders it in shared
+//                         memory, a 512x512 suppression bitmask is built from shared-memory box tiles and
+//                         reduced 64 candidates at a time with register bit operations.  It stops as soon
+//                         as max_output_size_per_class boxes are kept, exactly like TF's greedy loop, so
+//                         the reference's "no pre-NMS top-k" behaviour (trap T1) costs nothing extra.
+//   finalize_kernel       per image: merge classes by score, clip to [0,1], zero pad.
+#include "common.cuh"
+
+namespace frcnn {
+
+// ------------------------------------------------------------------------------------------------
+// Stage 1: decode + to_relative + background drop + score threshold.
+// boxes_rel is class-major [B,nc,N,4] so each NMS segment is contiguous; keys are the order-preserving
+// score keys (0 = not a candidate).  Boxes stay UNCLIPPED here (trap T2).
+// ------------------------------------------------------------------------------------------------
+template <bool kSingleClass>
+__global__ void __launch_bounds__(256)
+    decode_filter_kernel(float img_h, float img_w, const float4* __restrict__ regions, int regions_batched,
+                         const float* __restrict__ scores, const float4* __restrict__ deltas, int B, int N, int nc,
+                         float thr, float4* __restrict__ boxes_rel, uint32_t* __restrict__ keys) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)B * N * nc;
+    if (i >= total) return;
+    int c;
+    int64_t bn;
+    if (kSingleClass) {
+        c = 0;
+        bn = i;
+    } else {
+        c = (int)(i % nc);
+        bn = i / nc;
+    }
+    const int64_t n = bn % N;
+    const int64_t b = bn / N;
+    const float4 r = __ldg(regions + (regions_batched ? bn : n));
+    const float4 t = ld_nc_f4(deltas + i);
+    const float4 d = decode_box(t, r);                                                    // boxes.py:20-41
+    const float4 rel = make_float4(fdiv(d.x, img_w), fdiv(d.y, img_h), fdiv(d.z, img_w), fdiv(d.w, img_h));  // :86-93
+    float s;
+    if (kSingleClass) {
+        s = __ldg(reinterpret_cast<const float2*>(scores) + bn).y;  // [bg, fg] pair, one 8-byte load
+    } else {
+        s = __ldg(scores + bn * (nc + 1) + 1 + c);  // post_processing.py:52 drop background column
+    }
+    const int64_t o = (b * nc + c) * N + n;
+    boxes_rel[o] = rel;
+    keys[o] = (s > thr) ? score_key(s) : 0u;  // strict > (trap T3); NaN compares false
+}
+
+__global__ void score_keys_kernel(const float* __restrict__ scores, int64_t n, float thr, uint32_t* __restrict__ keys) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float s = scores[i];
+    keys[i] = (s > thr) ? score_key(s) : 0u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage 2: segmented greedy NMS.
+// ------------------------------------------------------------------------------------------------
+constexpr int kNmsThreads = 1024;
+constexpr int kChunk = 512;          // candidates ordered + resolved per iteration
+constexpr int kChunkWords = kChunk / 64;
+constexpr int kBins = 2048;          // 11-bit radix digits
+
+// TF CombinedNMS IOU on corner-normalised boxes with precomputed areas; returns iou > thr.
+__device__ __forceinline__ bool tf_suppresses(const float4& a, float area_a, const float4& b, float area_b, float thr) {
+    float iou = 0.0f;
+    if (!(area_a <= 0.0f || area_b <= 0.0f)) {
+        const float d0 = fmaxf(fsub(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.0f);
+        const float d1 = fmaxf(fsub(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.0f);
+        const float inter = fmul(d0, d1);
+        if (inter == 0.0f && thr >= 0.0f) return false;  // 0 / positive = 0, never > thr
+        iou = fdiv(inter, fsub(fadd(area_a, area_b), inter));
+    }
+    return iou > thr;
+}
+
+__device__ __forceinline__ uint64_t composite(uint32_t key, uint32_t idx) {
+    return (static_cast<uint64_t>(key) << 32) | static_cast<uint64_t>(0xffffffffu - idx);
+}
+
+struct NmsShared {
+    unsigned long long hi;        // exclusive upper bound of unvisited composites
+    unsigned long long pfx, pmask;
+    unsigned long long thresh;    // chunk = eligible composites >= thresh
+    int need, want, m, kept, budget, remaining, stop, select_done;
+    unsigned int cnt;
+    unsigned int alive32[kChunk / 32];
+};
+
+__global__ void __launch_bounds__(kNmsThreads, 1)
+    nms_select_kernel(const float4* __restrict__ boxes, const uint32_t* __restrict__ keys, int N, int cap, int top_n,
+                      float iou_thr, int32_t* __restrict__ kept_idx, int32_t* __restrict__ kept_count,
+                      int32_t* __restrict__ exhausted) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long* comp = reinterpret_cast<unsigned long long*>(smem_raw);             // [kChunk]
+    unsigned long long* mask = comp + kChunk;                                              // [kChunk*kChunkWords]
+    float4* cbox = reinterpret_cast<float4*>(mask + kChunk * kChunkWords);                  // [kChunk]
+    float4* kbox = cbox + kChunk;                                                          // [cap]
+    float* carea = reinterpret_cast<float*>(kbox + cap);                                    // [kChunk]
+    float* karea = carea + kChunk;                                                         // [cap]
+    unsigned int* hist = reinterpret_cast<unsigned int*>(karea + cap);                      // [kBins]
+    int* alive = reinterpret_cast<int*>(hist + kBins);                                      // [kChunk]
+    NmsShared* S = reinterpret_cast<NmsShared*>(alive + kChunk);
+
+    const int seg = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t* skeys = keys + (size_t)seg * N;
+    const float4* sboxes = boxes + (size_t)seg * N;
+    int32_t* sidx = kept_idx + (size_t)seg * cap;
+
+    if (tid == 0) {
+        S->hi = ~0ull;
+        S->kept = 0;
+        S->budget = top_n > 0 ? top_n : 0x7fffffff;
+        S->remaining = 0;
+        S->stop = 0;
+    }
+    int flag_exhausted = 0;
+    __syncthreads();
+
+    const int n_rounds = (N + kNmsThreads - 1) / kNmsThreads;
+
+    while (true) {
+        // ===================== SELECT: 11-bit MSD radix select on the 64-bit composite ==================
+        if (tid == 0) {
+            S->pfx = 0;
+            S->pmask = 0;
+            S->want = min(kChunk, S->budget);
+            S->need = S->want;
+            S->select_done = 0;
+            S->cnt = 0;
+        }
+        __syncthreads();
+        const unsigned long long hi = S->hi;
+        for (int pass = 0; pass < 5; ++pass) {
+            // digit layout: key bits 31..21, 20..10, 9..0 ; then ~idx bits 21..11, 10..0 (idx < 2^22)
+            const int shift = pass == 0 ? 53 : pass == 1 ? 42 : pass == 2 ? 32 : pass == 3 ? 11 : 0;
+            const int nb = pass == 2 ? 1024 : kBins;
+            for (int i = tid; i < nb; i += kNmsThreads) hist[i] = 0;
+            __syncthreads();
+            const unsigned long long pfx = S->pfx, pmask = S->pmask;
+            for (int r = 0; r < n_rounds; ++r) {
+                const int n = r * kNmsThreads + tid;
+                bool part = false;
+                unsigned int digit = 0;
+                if (n < N) {
+                    const uint32_t k = skeys[n];
+                    const unsigned long long c = composite(k, (uint32_t)n);
+                    part = (k != 0u) && (c < hi) && ((c & pmask) == pfx);
+                    digit = (unsigned int)(c >> shift) & (unsigned int)(nb - 1);
+                }
+                const unsigned act = __ballot_sync(0xffffffffu, part);
+                if (part) {  // warp-aggregated histogram update: one shared atomic per distinct digit
+                    const unsigned peers = __match_any_sync(act, digit);
+                    if (lane == __ffs(peers) - 1) atomicAdd(&hist[digit], (unsigned int)__popc(peers));
+                }
+            }
+            __syncthreads();
+            if (warp == 0) {
+                const int per = nb / 32;
+                const int top_bin = nb - 1 - lane * per;  // lane 0 owns the highest digits
+                unsigned int sum = 0;
+                for (int q = 0; q < per; ++q) sum += hist[top_bin - q];
+                unsigned int incl = sum;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
+                int need = S->need;
+                if (pass == 0) {  // total = all unvisited candidates of this segment
+                    if ((int)total < need) need = (int)total;
+                    if (lane == 0) {
+                        S->want = need;
+                        S->remaining = (int)total - need;
+                    }
+                }
+                const unsigned int excl = incl - sum;
+                if (need > 0 && excl < (unsigned)need && (unsigned)need <= incl) {  // exactly one lane
+                    unsigned int cum = excl;
+                    for (int q = 0; q < per; ++q) {
+                        const unsigned int h = hist[top_bin - q];
+                        if (cum + h >= (unsigned)need) {
+                            const unsigned long long bin = (unsigned long long)(top_bin - q);
+                            unsigned long long npfx = pfx | (bin << shift);
+                            unsigned long long nmask = pmask | ((unsigned long long)(nb - 1) << shift);
+                            const int in_bin = need - (int)cum;
+                            if ((int)h == in_bin) {  // whole bin taken: threshold found
+                                S->thresh = npfx;
+                                S->select_done = 1;
+                            } else if (pass == 2) {  // bits 22..31 of ~idx are constant ones
+                                npfx |= 0xffc00000ull;
+                                nmask |= 0xffc00000ull;
+                            }
+                            S->pfx = npfx;
+                            S->pmask = nmask;
+                            S->need = in_bin;
+                            break;
+                        }
+                        cum += h;
+                    }
+                }
+                if (need == 0 && lane == 0) S->select_done = 1;
+            }
+            __syncthreads();
+            if (S->select_done) break;
+        }
+        const int want = S->want;
+        if (want == 0) break;  // no candidates left (uniform)
+        const unsigned long long thresh = S->thresh;
+
+        // ===================== COLLECT the chunk (unordered) ===========================================
+        for (int r = 0; r < n_rounds; ++r) {
+            const int n = r * kNmsThreads + tid;
+            bool take = false;
+            unsigned long long c = 0;
+            if (n < N) {
+                const uint32_t k = skeys[n];
+                c = composite(k, (uint32_t)n);
+                take = (k != 0u) && (c < hi) && (c >= thresh);
+            }
+            const unsigned act = __ballot_sync(0xffffffffu, take);
+            if (act) {
+                unsigned int base = 0;
+                if (lane == 0) base = atomicAdd(&S->cnt, (unsigned int)__popc(act));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (take) {
+                    const unsigned int pos = base + __popc(act & ((1u << lane) - 1u));
+                    if (pos < (unsigned)kChunk) comp[pos] = c;
+                }
+            }
+        }
+        __syncthreads();
+        const int m = min((int)S->cnt, kChunk);  // == want by construction
+        int p2 = 32;
+        while (p2 < m) p2 <<= 1;
+        for (int i = m + tid; i < p2; i += kNmsThreads) comp[i] = 0ull;
+        __syncthreads();
+
+        // ===================== SORT descending (bitonic network in shared memory) =======================
+        for (int k = 2; k <= p2; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                if (tid < p2) {
+                    const int ixj = tid ^ j;
+                    if (ixj > tid) {
+                        const unsigned long long a = comp[tid], b = comp[ixj];
+                        const bool desc = (tid & k) == 0;
+                        if (desc ? (a < b) : (a > b)) {
+                            comp[tid] = b;
+                            comp[ixj] = a;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+
+        // ===================== LOAD boxes (corner-normalised) + areas ===================================
+        if (tid < kChunk) {
+            if (tid < m) {
+                const uint32_t idx = 0xffffffffu - (uint32_t)(comp[tid] & 0xffffffffull);
+                const float4 b = __ldg(sboxes + idx);
+                const float4 nb4 = make_float4(fminf(b.x, b.z), fminf(b.y, b.w), fmaxf(b.x, b.z), fmaxf(b.y, b.w));
+                cbox[tid] = nb4;
+                carea[tid] = fmul(fsub(nb4.z, nb4.x), fsub(nb4.w, nb4.y));
+                alive[tid] = 1;
+            } else {
+                alive[tid] = 0;
+            }
+        }
+        __syncthreads();
+
+        // ===================== PHASE A: chunk vs already kept boxes =====================================
+        {
+            const int kept = S->kept;
+            const int t = tid & (kChunk - 1), half = tid / kChunk;  // two threads per candidate
+            if (t < m && kept > 0) {
+                const float4 bt = cbox[t];
+                const float at = carea[t];
+                bool sup = false;
+                for (int j = half; j < kept; j += kNmsThreads / kChunk) {
+                    if (tf_suppresses(bt, at, kbox[j], karea[j], iou_thr)) {
+                        sup = true;
+                        break;
+                    }
+                }
+                if (sup) alive[t] = 0;
+            }
+        }
+        __syncthreads();
+        if (tid < kChunk) {
+            const unsigned bal = __ballot_sync(0xffffffffu, alive[tid] != 0);
+            if (lane == 0) S->alive32[warp] = bal;
+        }
+
+        // ===================== PHASE B: suppression bitmask among the chunk =============================
+        // mask[t][w] bit u: candidate 64w+u (ranked after t) overlaps t by more than the threshold.
+        for (int item = tid; item < m * kChunkWords; item += kNmsThreads) {
+            const int t = item / kChunkWords, w = item % kChunkWords;
+            unsigned long long bits = 0ull;
+            if (alive[t] && (w + 1) * 64 > t + 1 && w * 64 < m) {
+                const float4 bt = cbox[t];
+                const float at = carea[t];
+                const int u0 = max(w * 64, t + 1), u1 = min((w + 1) * 64, m);
+                for (int u = u0; u < u1; ++u)
+                    if (tf_suppresses(bt, at, cbox[u], carea[u], iou_thr)) bits |= 1ull << (u - w * 64);
+            }
+            mask[item] = bits;
+        }
+        __syncthreads();
+
+        // ===================== PHASE C: greedy resolve, 64 candidates at a time (warp 0) ===============
+        if (warp == 0) {
+            int kept = S->kept;
+            unsigned long long removed = 0ull;  // lane w < kChunkWords owns word w
+            const int nblk = (m + 63) / 64;
+            for (int blk = 0; blk < nblk && kept < cap; ++blk) {
+                const unsigned long long alive_w =
+                    (unsigned long long)S->alive32[2 * blk] | ((unsigned long long)S->alive32[2 * blk + 1] << 32);
+                unsigned long long cur = __shfl_sync(0xffffffffu, removed, blk) | ~alive_w;
+                // diagonal words of this block, two rows per lane
+                const int row0 = blk * 64 + lane, row1 = row0 + 32;
+                const unsigned long long d0 = row0 < m ? mask[row0 * kChunkWords + blk] : 0ull;
+                const unsigned long long d1 = row1 < m ? mask[row1 * kChunkWords + blk] : 0ull;
+                unsigned long long keepbits = 0ull;
+                int room = cap - kept;
+#pragma unroll
+                for (int i = 0; i < 64; ++i) {
+                    const unsigned long long di = __shfl_sync(0xffffffffu, i < 32 ? d0 : d1, i & 31);
+                    const bool take = !((cur >> i) & 1ull) && room > 0;
+                    if (take) {
+                        keepbits |= 1ull << i;
+                        cur |= di;
+                        --room;
+                    }
+                }
+                // append kept boxes (lane handles bits lane and lane+32)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int i = lane + 32 * h;
+                    if ((keepbits >> i) & 1ull) {
+                        const int pos = kept + __popcll(keepbits & ((1ull << i) - 1ull));
+                        const int row = blk * 64 + i;
+                        kbox[pos] = cbox[row];
+                        karea[pos] = carea[row];
+                        sidx[pos] = (int32_t)(0xffffffffu - (uint32_t)(comp[row] & 0xffffffffull));
+                    }
+                }
+                kept += __popcll(keepbits);
+                // fold the kept rows into the removed words of later blocks
+                unsigned long long kb = keepbits;
+                while (kb) {
+                    const int i = __ffsll((long long)kb) - 1;
+                    kb &= kb - 1ull;
+                    if (lane < kChunkWords) removed |= mask[(blk * 64 + i) * kChunkWords + lane];
+                }
+            }
+            if (lane == 0) {
+                S->kept = kept;
+                S->hi = comp[m - 1];
+                S->budget -= m;
+                int stop = 0;
+                if (kept >= cap) stop = 1;
+                else if (S->remaining == 0) stop = 1;                  // every candidate visited
+                else if (S->budget <= 0) stop = 2;                     // pre_nms_top_n cut the list short
+                S->stop = stop;
+            }
+        }
+        __syncthreads();
+        const int stop = S->stop;
+        if (stop) {
+            flag_exhausted = (stop == 2);
+            break;
+        }
+    }
+    __syncthreads();
+    const int kept = S->kept;
+    for (int i = kept + tid; i < cap; i += kNmsThreads) sidx[i] = -1;
+    if (tid == 0) {
+        kept_count[seg] = kept;
+        if (exhausted) exhausted[seg] = flag_exhausted;
+    }
+}
+
+static size_t nms_smem_bytes(int cap) {
+    return sizeof(unsigned long long) * (kChunk + kChunk * kChunkWords) + sizeof(float4) * (kChunk + (size_t)cap) +
+           sizeof(float) * (kChunk + (size_t)cap) + sizeof(unsigned int) * kBins + sizeof(int) * kChunk +
+           sizeof(NmsShared) + 16;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage 3: per image merge across classes (score desc, then class, then rank), clip, pad.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+    finalize_kernel(const float4* __restrict__ boxes_rel, const uint32_t* __restrict__ keys, int N, int nc, int cap,
+                    int R, const int32_t* __restrict__ kept_idx, const int32_t* __restrict__ kept_count,
+                    const int32_t* __restrict__ seg_exhausted, float4* __restrict__ out_boxes,
+                    float* __restrict__ out_scores, int32_t* __restrict__ out_classes, int32_t* __restrict__ out_valid,
+                    int32_t* __restrict__ out_idx, int32_t* __restrict__ out_exhausted, int p2) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long* comp = reinterpret_cast<unsigned long long*>(smem_raw);  // [p2] (nc > 1 only)
+    const int b = blockIdx.x, tid = threadIdx.x;
+    int total = 0;
+    for (int c = 0; c < nc; ++c) total += kept_count[b * nc + c];
+    const int nv = min(total, R);
+    if (nc > 1) {
+        for (int i = tid; i < p2; i += blockDim.x) {
+            unsigned long long v = 0ull;
+            const int c = i / cap, t = i % cap;
+            if (c < nc && t < kept_count[b * nc + c]) {
+                const int idx = kept_idx[((size_t)b * nc + c) * cap + t];
+                v = composite(keys[((size_t)b * nc + c) * N + idx], (uint32_t)i);  // ord = c*cap + t
+            }
+            comp[i] = v;
+        }
+        __syncthreads();
+        for (int k = 2; k <= p2; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < p2; t += blockDim.x) {
+                    const int ixj = t ^ j;
+                    if (ixj > t) {
+                        const unsigned long long a = comp[t], bb = comp[ixj];
+                        const bool desc = (t & k) == 0;
+                        if (desc ? (a < bb) : (a > bb)) {
+                            comp[t] = bb;
+                            comp[ixj] = a;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+    }
+    for (int t = tid; t < R; t += blockDim.x) {
+        float4 ob = make_float4(0.f, 0.f, 0.f, 0.f);
+        float os = 0.f;
+        int oc = 0, oi = -1;
+        if (t < nv) {
+            int c = 0, rank = t;
+            if (nc > 1) {
+                const uint32_t ord = 0xffffffffu - (uint32_t)(comp[t] & 0xffffffffull);
+                c = (int)(ord / (uint32_t)cap);
+                rank = (int)(ord % (uint32_t)cap);
+            }
+            const size_t seg = (size_t)b * nc + c;
+            oi = kept_idx[seg * cap + rank];
+            const float4 v = boxes_rel[seg * N + oi];
+            ob = make_float4(fmaxf(fminf(v.x, 1.f), 0.f), fmaxf(fminf(v.y, 1.f), 0.f), fmaxf(fminf(v.z, 1.f), 0.f),
+                             fmaxf(fminf(v.w, 1.f), 0.f));  // clip_boxes=True
+            os = key_score(keys[seg * N + oi]);
+            oc = c;
+        }
+        out_boxes[(size_t)b * R + t] = ob;
+        out_scores[(size_t)b * R + t] = os;
+        out_classes[(size_t)b * R + t] = oc;
+        if (out_idx) out_idx[(size_t)b * R + t] = oi;
+    }
+    if (tid == 0) {
+        out_valid[b] = nv;
+        if (out_exhausted) {
+            int e = 0;
+            for (int c = 0; c < nc; ++c) e |= seg_exhausted[b * nc + c];
+            out_exhausted[b] = e;
+        }
+    }
+}
+
+// workspace layout for postprocess: boxes_rel | keys | kept_idx | kept_count | exhausted
+struct PostWs {
+    float4* boxes_rel;
+    uint32_t* keys;
+    int32_t* kept_idx;
+    int32_t* kept_count;
+    int32_t* exhausted;
+    size_t bytes;
+};
+static PostWs carve_post_ws(void* base, int B, int N, int nc, int cap) {
+    PostWs w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        void* p = base ? static_cast<char*>(base) + off : nullptr;
+        off += align_up(bytes, 256);
+        return p;
+    };
+    const size_t segs = (size_t)B * nc;
+    w.boxes_rel = static_cast<float4*>(take(sizeof(float4) * segs * N));
+    w.keys = static_cast<uint32_t*>(take(sizeof(uint32_t) * segs * N));
+    w.kept_idx = static_cast<int32_t*>(take(sizeof(int32_t) * segs * (size_t)(cap > 0 ? cap : 1)));
+    w.kept_count = static_cast<int32_t*>(take(sizeof(int32_t) * segs));
+    w.exhausted = static_cast<int32_t*>(take(sizeof(int32_t) * segs));
+    w.bytes = off;
+    return w;
+}
+
+static int launch_nms(const float4* boxes, const uint32_t* keys, int segments, int N, int cap, int top_n, float iou_thr,
+                      int32_t* kept_idx, int32_t* kept_count, int32_t* exhausted, cudaStream_t st) {
+    FRCNN_REQUIRE(cap <= 4096, FRCNN_ELIMIT, "nms: min(max_output, N) = %d exceeds the 4096 limit", cap);
+    FRCNN_REQUIRE(N < (1 << 22), FRCNN_ELIMIT, "nms: N = %d exceeds the 2^22 limit", N);
+    const size_t smem = nms_smem_bytes(cap);
+    static thread_local size_t configured = 0;
+    if (smem > configured) {
+        FRCNN_CUDA(cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    nms_select_kernel<<<segments, kNmsThreads, smem, st>>>(boxes, keys, N, cap, top_n, iou_thr, kept_idx, kept_count,
+                                                           exhausted);
+    FRCNN_LAUNCH_CHECK("nms_select_kernel");
+    return 0;
+}
+
+}  // namespace frcnn
+
+using namespace frcnn;
+
+extern "C" {
+
+size_t frcnn_postprocess_workspace_bytes(int B, int N, int nc, int max_per_class, int /*max_total*/) {
+    if (B <= 0 || N < 0 || nc <= 0) return 0;
+    const int cap = max_per_class < N ? max_per_class : N;
+    return carve_post_ws(nullptr, B, N, nc, cap).bytes;
+}
+
+int frcnn_decode_filter(float img_h, float img_w, const float* regions, int regions_batched, const float* pred_scores,
+                        const float* pred_boxes, int B, int N, int nc, float score_threshold, float* boxes_rel,
+                        uint32_t* keys, frcnn_stream_t stream) {
+    FRCNN_REQUIRE(B > 0 && N >= 0 && nc > 0, FRCNN_EINVAL, "decode_filter: bad shape B=%d N=%d nc=%d", B, N, nc);
+    FRCNN_REQUIRE(aligned16(regions) && aligned16(pred_boxes) && aligned16(boxes_rel) &&
+                      (reinterpret_cast<uintptr_t>(pred_scores) & 7u) == 0,
+                  FRCNN_EINVAL, "decode_filter: pointers must be 16-byte aligned");
+    const int64_t total = (int64_t)B * N * nc;
+    if (total == 0) return 0;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (nc == 1)
+        decode_filter_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(img_h, img_w, (const float4*)regions,
+                                                                        regions_batched, pred_scores,
+                                                                        (const float4*)pred_boxes, B, N, nc,
+                                                                        score_threshold, (float4*)boxes_rel, keys);
+    else
+        decode_filter_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(img_h, img_w, (const float4*)regions,
+                                                                         regions_batched, pred_scores,
+                                                                         (const float4*)pred_boxes, B, N, nc,
+                                                                         score_threshold, (float4*)boxes_rel, keys);
+    FRCNN_LAUNCH_CHECK("decode_filter_kernel");
+    return 0;
+}
+
+size_t frcnn_nms_workspace_bytes(int segments, int N) {
+    if (segments <= 0 || N < 0) return 0;
+    return align_up(sizeof(uint32_t) * (size_t)segments * N, 256);
+}
+
+int frcnn_nms(const float* boxes, const float* scores, int segments, int N, float score_threshold, float iou_threshold,
+              int max_output, int pre_nms_top_n, int32_t* kept_idx, int32_t* kept_count, int32_t* exhausted,
+              void* workspace, size_t workspace_bytes, frcnn_stream_t stream) {
+    FRCNN_REQUIRE(segments > 0 && N >= 0 && max_output >= 0, FRCNN_EINVAL, "nms: bad shape");
+    FRCNN_REQUIRE(aligned16(boxes) && kept_idx && kept_count, FRCNN_EINVAL, "nms: bad pointers");
+    FRCNN_REQUIRE(workspace_bytes >= frcnn_nms_workspace_bytes(segments, N) && (workspace || N == 0), FRCNN_EWORKSPACE,
+                  "nms: workspace too small");
+    const int cap = max_output < N ? max_output : N;
+    uint32_t* keys = static_cast<uint32_t*>(workspace);
+    const int64_t total = (int64_t)segments * N;
+    if (total > 0) {
+        score_keys_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(scores, total,
+                                                                                         score_threshold, keys);
+        FRCNN_LAUNCH_CHECK("score_keys_kernel");
+    }
+    return launch_nms((const float4*)boxes, keys, segments, N, cap, pre_nms_top_n, iou_threshold, kept_idx, kept_count,
+                      exhausted, as_stream(stream));
+}
+
+int frcnn_postprocess(float img_h, float img_w, const float* regions, int regions_batched, const float* pred_scores,
+                      const float* pred_boxes, int B, int N, int nc, float score_threshold, float iou_threshold,
+                      int max_per_class, int max_total, int pre_nms_top_n, float* out_boxes, float* out_scores,
+                      int32_t* out_classes, int32_t* out_valid, int32_t* out_idx, int32_t* out_exhausted,
+                      void* workspace, size_t workspace_bytes, frcnn_stream_t stream) {
+    FRCNN_REQUIRE(B > 0 && N >= 0 && nc > 0 && max_per_class >= 0 && max_total > 0, FRCNN_EINVAL,
+                  "postprocess: bad shape B=%d N=%d nc=%d per_class=%d total=%d", B, N, nc, max_per_class, max_total);
+    FRCNN_REQUIRE(aligned16(out_boxes) && out_scores && out_classes && out_valid, FRCNN_EINVAL,
+                  "postprocess: bad output pointers");
+    const int cap = max_per_class < N ? max_per_class : N;  // min(max_output_size_per_class, num_boxes) (T17)
+    FRCNN_REQUIRE((int64_t)nc * cap <= 16384, FRCNN_ELIMIT, "postprocess: nc*cap = %lld exceeds the 16384 limit",
+                  (long long)nc * cap);
+    FRCNN_REQUIRE(workspace_bytes >= frcnn_postprocess_workspace_bytes(B, N, nc, max_per_class, max_total) && workspace,
+                  FRCNN_EWORKSPACE, "postprocess: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    PostWs w = carve_post_ws(workspace, B, N, nc, cap);
+    int rc = frcnn_decode_filter(img_h, img_w, regions, regions_batched, pred_scores, pred_boxes, B, N, nc,
+                                 score_threshold, (float*)w.boxes_rel, w.keys, stream);
+    if (rc) return rc;
+    rc = launch_nms(w.boxes_rel, w.keys, B * nc, N, cap, pre_nms_top_n, iou_threshold, w.kept_idx, w.kept_count,
+                    w.exhausted, st);
+    if (rc) return rc;
+    int p2 = 0;
+    size_t smem = 0;
+    if (nc > 1) {
+        p2 = 32;
+        while (p2 < nc * cap) p2 <<= 1;
+        smem = sizeof(unsigned long long) * (size_t)p2;
+        static thread_local size_t configured = 0;
+        if (smem > 48 * 1024 && smem > configured) {
+            FRCNN_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+    }
+    finalize_kernel<<<B, nc > 1 ? 1024 : 256, smem, st>>>(w.boxes_rel, w.keys, N, nc, cap > 0 ? cap : 1, max_total,
+                                                          w.kept_idx, w.kept_count, w.exhausted, (float4*)out_boxes,
+                                                          out_scores, out_classes, out_valid, out_idx, out_exhausted,
+                                                          p2);
+    FRCNN_LAUNCH_CHECK("finalize_kernel");
+    return 0;
+}
+
+}  // extern "C"

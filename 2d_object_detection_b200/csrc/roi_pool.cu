@@ -1,0 +1,253 @@
+// RoI pooling: models/detectors/fast_rcnn_detector.py:133-177 (ROIPooling) forward and the backward that
+// tf.GradientTape derives for it (models/faster_rcnn.py:73,103): tf.image.crop_and_resize to S x S
+// (S = pooled_size * kernel_size, one bilinear sample per crop pixel, (H-1) scaling, extrapolation 0)
+// fused with MaxPool2D(kernel_size), never materialising the S x S crop (traps T6-T8).
+//
+// Layout: feature maps NHWC, so the 4 neighbours of a sample are 4 contiguous C-float rows; a thread
+// owns one float4 of channels and walks the bins of one RoI, so every global access is a coalesced
+// 128-bit load/store.  Arithmetic follows the TF CPU kernel operation by operation with explicit _rn
+// intrinsics: the forward result is bit-identical to the CPU oracle.
+#include "common.cuh"
+
+namespace frcnn {
+
+constexpr int kMaxCrop = 32;  // S = P*k <= 32
+constexpr int kRoiThreads = 256;
+
+struct AxisTab {
+    int lo[kMaxCrop];
+    int hi[kMaxCrop];
+    float lerp[kMaxCrop];
+    int valid[kMaxCrop];
+};
+
+// Sampling position i of crop_and_resize along one axis; op order of crop_and_resize_op.cc.
+__device__ __forceinline__ void axis_sample(float c1, float c2, int extent, int S, int i, AxisTab& t) {
+    const float em1 = (float)(extent - 1);
+    float in;
+    if (S > 1) {
+        const float scale = fdiv(fmul(fsub(c2, c1), em1), (float)(S - 1));
+        in = fadd(fmul(c1, em1), fmul((float)i, scale));
+    } else {
+        in = fmul(fmul(0.5f, fadd(c1, c2)), em1);
+    }
+    const bool ok = (in >= 0.0f) && (in <= em1);  // NaN -> not sampled
+    t.valid[i] = ok ? 1 : 0;
+    const float fl = ok ? floorf(in) : 0.0f;
+    t.lo[i] = (int)fl;
+    t.hi[i] = ok ? (int)ceilf(in) : 0;
+    t.lerp[i] = ok ? fsub(in, fl) : 0.0f;
+}
+
+// ---- tiny vector abstraction: float4 (C % 4 == 0) or float -------------------------------------
+__device__ __forceinline__ float4 vload(const float4* p) { return __ldg(p); }
+__device__ __forceinline__ float vload(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float4 vzero(float4) { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float vzero(float) { return 0.f; }
+__device__ __forceinline__ float lerp1(float a, float b, float w) { return fadd(a, fmul(fsub(b, a), w)); }
+__device__ __forceinline__ float lerpv(float a, float b, float w) { return lerp1(a, b, w); }
+__device__ __forceinline__ float4 lerpv(const float4& a, const float4& b, float w) {
+    return make_float4(lerp1(a.x, b.x, w), lerp1(a.y, b.y, w), lerp1(a.z, b.z, w), lerp1(a.w, b.w, w));
+}
+__device__ __forceinline__ void vstore_stream(float4* p, const float4& v) { st_cs_f4(p, v); }
+__device__ __forceinline__ void vstore_stream(float* p, float v) { __stcs(p, v); }
+
+// One bilinear sample (crop pixel) for this thread's channels: top = TL + (TR-TL)*xl, etc.
+template <typename V>
+__device__ __forceinline__ V bilinear(const V* __restrict__ fb, int Wf, int CV, int ylo, int yhi, float yl, int xlo,
+                                      int xhi, float xl, int cv) {
+    const V tl = vload(fb + ((size_t)ylo * Wf + xlo) * CV + cv);
+    const V tr = vload(fb + ((size_t)ylo * Wf + xhi) * CV + cv);
+    const V bl = vload(fb + ((size_t)yhi * Wf + xlo) * CV + cv);
+    const V br = vload(fb + ((size_t)yhi * Wf + xhi) * CV + cv);
+    const V top = lerpv(tl, tr, xl);
+    const V bot = lerpv(bl, br, xl);
+    return lerpv(top, bot, yl);
+}
+
+__device__ __forceinline__ void max_first(float& best, float v, int& arg, int s) {
+    if (v > best) {  // strict: the first maximum in row-major window order wins (T8)
+        best = v;
+        arg = s;
+    }
+}
+
+template <typename V>
+__global__ void __launch_bounds__(kRoiThreads)
+    roi_pool_fwd_kernel(const V* __restrict__ feat, int Hf, int Wf, int CV, const float4* __restrict__ rois, int R, int P,
+                        int k, V* __restrict__ out) {
+    __shared__ AxisTab ty, tx;
+    const int r = blockIdx.x, b = blockIdx.y;
+    const int S = P * k;
+    const float4 roi = rois[(size_t)b * R + r];  // x1,y1,x2,y2 (fast_rcnn_detector.py:157-158 reorders for TF)
+    if (threadIdx.x < S) axis_sample(roi.y, roi.w, Hf, S, threadIdx.x, ty);
+    else if (threadIdx.x >= 32 && threadIdx.x < 32 + S) axis_sample(roi.x, roi.z, Wf, S, threadIdx.x - 32, tx);
+    __syncthreads();
+    const V* fb = feat + (size_t)b * Hf * Wf * CV;
+    V* ob = out + ((size_t)b * R + r) * P * P * CV;
+    for (int cv = threadIdx.x; cv < CV; cv += blockDim.x) {
+        for (int py = 0; py < P; ++py)
+            for (int px = 0; px < P; ++px) {
+                V best = vzero(V());
+                bool first = true;
+                for (int dy = 0; dy < k; ++dy) {
+                    const int sy = py * k + dy;
+                    for (int dx = 0; dx < k; ++dx) {
+                        const int sx = px * k + dx;
+                        V v = vzero(V());  // extrapolation_value = 0
+                        if (ty.valid[sy] && tx.valid[sx])
+                            v = bilinear(fb, Wf, CV, ty.lo[sy], ty.hi[sy], ty.lerp[sy], tx.lo[sx], tx.hi[sx],
+                                         tx.lerp[sx], cv);
+                        if (first) {
+                            best = v;
+                            first = false;
+                        } else {
+                            if constexpr (sizeof(V) == 16) {
+                                best.x = v.x > best.x ? v.x : best.x;
+                                best.y = v.y > best.y ? v.y : best.y;
+                                best.z = v.z > best.z ? v.z : best.z;
+                                best.w = v.w > best.w ? v.w : best.w;
+                            } else {
+                                best = v > best ? v : best;
+                            }
+                        }
+                    }
+                }
+                vstore_stream(ob + ((size_t)py * P + px) * CV + cv, best);
+            }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward.  Each thread re-derives the arg-max sample of its bins from the feature map (no saved
+// state), then scatters the four bilinear weights with 16-byte vector reductions (red.global.add.v4.f32).
+// Channels whose arg-max is a different sample of the window contribute an exact 0 to that reduction.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add(float4* p, const float4& v) { red_add_f4(p, v); }
+__device__ __forceinline__ void red_add(float* p, float v) { atomicAdd(p, v); }
+__device__ __forceinline__ float4 vscale(const float4& a, float w) {
+    return make_float4(fmul(w, a.x), fmul(w, a.y), fmul(w, a.z), fmul(w, a.w));
+}
+__device__ __forceinline__ float vscale(float a, float w) { return fmul(w, a); }
+
+template <typename V>
+__global__ void __launch_bounds__(kRoiThreads)
+    roi_pool_bwd_kernel(const V* __restrict__ feat, int Hf, int Wf, int CV, const float4* __restrict__ rois, int R, int P,
+                        int k, const V* __restrict__ dy_in, V* __restrict__ dfeat) {
+    __shared__ AxisTab ty, tx;
+    const int r = blockIdx.x, b = blockIdx.y;
+    const int S = P * k;
+    const float4 roi = rois[(size_t)b * R + r];
+    if (threadIdx.x < S) axis_sample(roi.y, roi.w, Hf, S, threadIdx.x, ty);
+    else if (threadIdx.x >= 32 && threadIdx.x < 32 + S) axis_sample(roi.x, roi.z, Wf, S, threadIdx.x - 32, tx);
+    __syncthreads();
+    const V* fb = feat + (size_t)b * Hf * Wf * CV;
+    V* gb = dfeat + (size_t)b * Hf * Wf * CV;
+    const V* gy = dy_in + ((size_t)b * R + r) * P * P * CV;
+    constexpr int kLanes = sizeof(V) / 4;
+    for (int cv = threadIdx.x; cv < CV; cv += blockDim.x) {
+        for (int py = 0; py < P; ++py)
+            for (int px = 0; px < P; ++px) {
+                float best[kLanes];
+                int arg[kLanes];
+                for (int dy = 0; dy < k; ++dy)
+                    for (int dx = 0; dx < k; ++dx) {
+                        const int sy = py * k + dy, sx = px * k + dx, s = dy * k + dx;
+                        V v = vzero(V());
+                        if (ty.valid[sy] && tx.valid[sx])
+                            v = bilinear(fb, Wf, CV, ty.lo[sy], ty.hi[sy], ty.lerp[sy], tx.lo[sx], tx.hi[sx],
+                                         tx.lerp[sx], cv);
+                        const float* vf = reinterpret_cast<const float*>(&v);
+#pragma unroll
+                        for (int l = 0; l < kLanes; ++l) {
+                            if (s == 0) {
+                                best[l] = vf[l];
+                                arg[l] = 0;
+                            } else {
+                                max_first(best[l], vf[l], arg[l], s);
+                            }
+                        }
+                    }
+                V g;
+                if constexpr (kLanes == 4) g = ld_nc_f4(gy + ((size_t)py * P + px) * CV + cv);
+                else g = __ldg(gy + ((size_t)py * P + px) * CV + cv);
+                const float* gf = reinterpret_cast<const float*>(&g);
+                for (int dy = 0; dy < k; ++dy)
+                    for (int dx = 0; dx < k; ++dx) {
+                        const int sy = py * k + dy, sx = px * k + dx, s = dy * k + dx;
+                        if (!(ty.valid[sy] && tx.valid[sx])) continue;  // out-of-range samples contribute nothing
+                        V gs;
+                        float* gsf = reinterpret_cast<float*>(&gs);
+                        bool any = false;
+#pragma unroll
+                        for (int l = 0; l < kLanes; ++l) {
+                            const bool sel = arg[l] == s;
+                            gsf[l] = sel ? gf[l] : 0.0f;
+                            any |= sel;
+                        }
+                        if (!any) continue;
+                        const float yl = ty.lerp[sy], xl = tx.lerp[sx];
+                        const V dtop = vscale(gs, fsub(1.0f, yl));
+                        V* top = gb + ((size_t)ty.lo[sy] * Wf) * CV + cv;
+                        red_add(top + (size_t)tx.lo[sx] * CV, vscale(dtop, fsub(1.0f, xl)));
+                        if (xl != 0.0f) red_add(top + (size_t)tx.hi[sx] * CV, vscale(dtop, xl));
+                        if (yl != 0.0f) {
+                            const V dbot = vscale(gs, yl);
+                            V* bot = gb + ((size_t)ty.hi[sy] * Wf) * CV + cv;
+                            red_add(bot + (size_t)tx.lo[sx] * CV, vscale(dbot, fsub(1.0f, xl)));
+                            if (xl != 0.0f) red_add(bot + (size_t)tx.hi[sx] * CV, vscale(dbot, xl));
+                        }
+                    }
+            }
+    }
+}
+
+}  // namespace frcnn
+
+using namespace frcnn;
+
+extern "C" {
+
+int frcnn_roi_pool_forward(const float* feat, int B, int Hf, int Wf, int C, const float* rois, int R, int P, int k,
+                           float* out, frcnn_stream_t stream) {
+    FRCNN_REQUIRE(B > 0 && Hf > 0 && Wf > 0 && C > 0 && R >= 0 && P > 0 && k > 0, FRCNN_EINVAL,
+                  "roi_pool_forward: bad shape");
+    FRCNN_REQUIRE(P * k <= kMaxCrop, FRCNN_ELIMIT, "roi_pool_forward: pooled_size*kernel_size = %d > %d", P * k, kMaxCrop);
+    FRCNN_REQUIRE(aligned16(feat) && aligned16(rois) && aligned16(out), FRCNN_EINVAL,
+                  "roi_pool_forward: pointers must be 16-byte aligned");
+    FRCNN_REQUIRE(B <= 65535, FRCNN_ELIMIT, "roi_pool_forward: B > 65535");
+    if (R == 0) return 0;
+    const dim3 grid(R, B);
+    if (C % 4 == 0)
+        roi_pool_fwd_kernel<float4><<<grid, kRoiThreads, 0, as_stream(stream)>>>((const float4*)feat, Hf, Wf, C / 4,
+                                                                                  (const float4*)rois, R, P, k,
+                                                                                  (float4*)out);
+    else
+        roi_pool_fwd_kernel<float><<<grid, kRoiThreads, 0, as_stream(stream)>>>(feat, Hf, Wf, C, (const float4*)rois, R,
+                                                                                 P, k, out);
+    FRCNN_LAUNCH_CHECK("roi_pool_fwd_kernel");
+    return 0;
+}
+
+int frcnn_roi_pool_backward(const float* feat, int B, int Hf, int Wf, int C, const float* rois, int R, int P, int k,
+                            const float* dy, float* dfeat, frcnn_stream_t stream) {
+    FRCNN_REQUIRE(B > 0 && Hf > 0 && Wf > 0 && C > 0 && R >= 0 && P > 0 && k > 0, FRCNN_EINVAL,
+                  "roi_pool_backward: bad shape");
+    FRCNN_REQUIRE(P * k <= kMaxCrop, FRCNN_ELIMIT, "roi_pool_backward: pooled_size*kernel_size = %d > %d", P * k, kMaxCrop);
+    FRCNN_REQUIRE(aligned16(feat) && aligned16(rois) && aligned16(dy) && aligned16(dfeat), FRCNN_EINVAL,
+                  "roi_pool_backward: pointers must be 16-byte aligned");
+    FRCNN_REQUIRE(B <= 65535, FRCNN_ELIMIT, "roi_pool_backward: B > 65535");
+    FRCNN_CUDA(cudaMemsetAsync(dfeat, 0, sizeof(float) * (size_t)B * Hf * Wf * C, as_stream(stream)));
+    if (R == 0) return 0;
+    const dim3 grid(R, B);
+    if (C % 4 == 0)
+        roi_pool_bwd_kernel<float4><<<grid, kRoiThreads, 0, as_stream(stream)>>>(
+            (const float4*)feat, Hf, Wf, C / 4, (const float4*)rois, R, P, k, (const float4*)dy, (float4*)dfeat);
+    else
+        roi_pool_bwd_kernel<float><<<grid, kRoiThreads, 0, as_stream(stream)>>>(feat, Hf, Wf, C, (const float4*)rois, R,
+                                                                                 P, k, dy, dfeat);
+    FRCNN_LAUNCH_CHECK("roi_pool_bwd_kernel");
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,75 @@
+"""``ROIPooling`` of the reference's models/detectors/fast_rcnn_detector.py:133-177, differentiable w.r.t. the
+feature maps (the gradient TF's tape derives at models/faster_rcnn.py:103).  The Dense heads are out of scope.
+"""
+from __future__ import annotations
+
+import torch
+
+from ..._tensor import as_device, check, lib, ptr, stream
+
+
+def roi_pool_forward(feature_maps, rois, pooled_size, kernel_size):
+    """crop_and_resize(S=P*k) + MaxPool2D(k) fused: feature_maps [B,Hf,Wf,C], rois [B,R,4] rel x1,y1,x2,y2
+    -> [B,R,P,P,C]."""
+    f, r = as_device(feature_maps), as_device(rois)
+    if f.dim() != 4 or r.dim() != 3 or r.shape[-1] != 4 or r.shape[0] != f.shape[0]:
+        raise ValueError(f"feature_maps [B,H,W,C] / rois [B,R,4] expected, got {tuple(f.shape)} / {tuple(r.shape)}")
+    B, Hf, Wf, C = f.shape
+    R = r.shape[1]
+    P, k = int(pooled_size), int(kernel_size)
+    out = torch.empty((B, R, P, P, C), dtype=torch.float32, device=f.device)
+    check(lib().frcnn_roi_pool_forward(ptr(f), B, Hf, Wf, C, ptr(r), R, P, k, ptr(out), stream()), "roi_pool_forward")
+    return out
+
+
+def roi_pool_backward(feature_maps, rois, dy, pooled_size, kernel_size):
+    """Gradient of roi_pool_forward w.r.t. feature_maps: dy [B,R,P,P,C] (any shape with that many elements)."""
+    f, r = as_device(feature_maps), as_device(rois)
+    B, Hf, Wf, C = f.shape
+    R = r.shape[1]
+    P, k = int(pooled_size), int(kernel_size)
+    g = as_device(dy)
+    if g.numel() != B * R * P * P * C:
+        raise ValueError(f"dy has {g.numel()} elements, expected {B * R * P * P * C}")
+    df = torch.empty_like(f)
+    check(lib().frcnn_roi_pool_backward(ptr(f), B, Hf, Wf, C, ptr(r), R, P, k, ptr(g), ptr(df), stream()),
+          "roi_pool_backward")
+    return df
+
+
+class _ROIPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feature_maps, rois, pooled_size, kernel_size):
+        ctx.save_for_backward(feature_maps, rois)
+        ctx.pk = (pooled_size, kernel_size)
+        return roi_pool_forward(feature_maps, rois, pooled_size, kernel_size)
+
+    @staticmethod
+    def backward(ctx, dy):
+        feature_maps, rois = ctx.saved_tensors
+        # no box gradient: the proposals are stop_gradient-ed in the reference (post_processing.py:58)
+        return roi_pool_backward(feature_maps, rois, dy.contiguous(), *ctx.pk), None, None, None
+
+
+class ROIPooling:
+    """fast_rcnn_detector.py:133-177.  ``ROIPooling(pooled_size, kernel_size)``; ``call(feature_maps, rois,
+    flatten=False, keep_batch_dim=False)`` (also ``__call__``), as ``FastRCNNDetector`` uses it (:23, :60)."""
+
+    def __init__(self, pooled_size, kernel_size, **kwargs):
+        self._pooled_size = int(pooled_size)
+        self._kernel_size = int(kernel_size)
+        self.name = kwargs.get("name", "regions_of_interest_pooling")
+
+    def call(self, feature_maps, rois, flatten=False, keep_batch_dim=False):
+        f, r = as_device(feature_maps), as_device(rois)
+        if isinstance(feature_maps, torch.Tensor) and feature_maps.requires_grad:
+            f = feature_maps if feature_maps.is_cuda and feature_maps.is_contiguous() else f
+        pooled = _ROIPoolFn.apply(f, r, self._pooled_size, self._kernel_size)  # [B,R,P,P,C]
+        B, R = r.shape[0], r.shape[1]
+        if flatten:  # Flatten in (py, px, c) order (:170-171) -- a view, nothing is copied
+            pooled = pooled.reshape(B, R, -1)
+        if not keep_batch_dim:  # the reference regroups with split/stack (:173-175); here it is a reshape
+            pooled = pooled.reshape((B * R,) + tuple(pooled.shape[2:]))
+        return pooled
+
+    __call__ = call

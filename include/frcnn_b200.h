@@ -1,0 +1,177 @@
+/*
+ * frcnn_b200.h -- C ABI of libfrcnn_b200.so: the B200 (sm_100a) implementation of the
+ * region-proposal / RoI hot path of antoineBarbez/2D_object_detection.
+ *
+ * The reference has no FFI of its own (it is pure Python on TensorFlow 2); the entry points
+ * below are what a binding for this path replaces, one per reference callable.  Each cites the
+ * reference interface (file:line under the reference repository) whose results it reproduces.
+ * INTEGRATION.md shows the reference-side stubs.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  Unless a parameter is marked HOST, every pointer is a DEVICE
+ *    pointer owned by the caller, fp32 C-contiguous, 16-byte aligned.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Functions only
+ *    enqueue work on it: no allocation, no device synchronisation, re-entrant per stream.
+ *    (Exception: the frcnn_pipeline_* host-buffer API owns its device buffers and synchronises.)
+ *  - Scratch memory comes from the caller: frcnn_<op>_workspace_bytes() then `workspace`.
+ *  - Return value: 0 on success; a positive cudaError_t, or a negative FRCNN_E* code.
+ *    frcnn_last_error() returns a thread-local description of the last failure.
+ *  - Box layout everywhere: [x_min, y_min, x_max, y_max]; "abs" = pixels, "rel" = divided by W/H.
+ *  - All arithmetic is fp32 in the reference's operation order, compiled without FMA contraction.
+ */
+#ifndef FRCNN_B200_H_
+#define FRCNN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRCNN_VERSION 100 /* 0.1.0 */
+
+#define FRCNN_EINVAL (-1)    /* bad argument (shape, alignment, limit) */
+#define FRCNN_EWORKSPACE (-2) /* workspace too small */
+#define FRCNN_ELIMIT (-3)    /* size beyond a documented limit of this build */
+
+typedef void* frcnn_stream_t;
+
+#if defined(__GNUC__)
+#define FRCNN_API __attribute__((visibility("default")))
+#else
+#define FRCNN_API
+#endif
+
+FRCNN_API int frcnn_version(void);
+FRCNN_API const char* frcnn_last_error(void);
+
+/* ---- utils/boxes.py ---------------------------------------------------------------------- */
+
+/* clip_to_window(boxes, window)  utils/boxes.py:4-17; window = x_min,y_min,x_max,y_max (:13). */
+FRCNN_API int frcnn_clip_to_window(const float* boxes, int64_t n_boxes, float win_x_min, float win_y_min, float win_x_max,
+                         float win_y_max, float* out, frcnn_stream_t stream);
+
+/* decode(boxes, reference_boxes)  utils/boxes.py:20-41.  Reference box of element i is
+ * refs[(i / ref_inner) % ref_period] (covers [N,4] regions tiled over batch and classes). */
+FRCNN_API int frcnn_decode(const float* deltas, const float* refs, int64_t n_boxes, int64_t ref_inner, int64_t ref_period,
+                 float* out, frcnn_stream_t stream);
+
+/* encode(boxes, reference_boxes)  utils/boxes.py:44-73. Same reference indexing as frcnn_decode. */
+FRCNN_API int frcnn_encode(const float* boxes, const float* refs, int64_t n_boxes, int64_t ref_inner, int64_t ref_period,
+                 float* out, frcnn_stream_t stream);
+
+/* to_absolute (divide = 0, multiplies) / to_relative (divide = 1, true division) utils/boxes.py:76-93. */
+FRCNN_API int frcnn_scale_boxes(const float* boxes, int64_t n_boxes, float image_height, float image_width, int divide,
+                      float* out, frcnn_stream_t stream);
+
+/* ---- models/detectors/rpn_detector.py ------------------------------------------------------ */
+
+/* RPNDetector._generate_anchors  rpn_detector.py:162-199.  scales/aspect_ratios are HOST arrays
+ * (ns * nr <= 64).  anchors_out: [Hf*Wf*ns*nr, 4] abs, index (i*Wf + j)*A + (r*ns + s). */
+FRCNN_API int frcnn_generate_anchors(int grid_h, int grid_w, const float* scales /*HOST*/, int ns,
+                           const float* aspect_ratios /*HOST*/, int nr, float base_h, float base_w, float stride_h,
+                           float stride_w, float* anchors_out, frcnn_stream_t stream);
+
+/* RPNDetector._remove_invalid_anchors_and_predictions index list  rpn_detector.py:215-224:
+ * ascending indices of anchors with x0>=0, y0>=0, x1<=W, y1<=H.  idx_out [n] int64 (first *count_out
+ * entries valid), count_out [1] int32, both device. */
+FRCNN_API int frcnn_valid_anchor_indices(const float* anchors, int64_t n, float image_height, float image_width,
+                               int64_t* idx_out, int32_t* count_out, frcnn_stream_t stream);
+
+/* gather rows: out[b, m, :] = in[b, idx[m], :] (tf.gather(axis=1) at rpn_detector.py:226-228);
+ * row_floats floats per row; idx int64 [m] device.  batch = 1 gathers the anchors. */
+FRCNN_API int frcnn_gather_rows(const float* in, int64_t batch, int64_t n, int64_t row_floats, const int64_t* idx, int64_t m,
+                      float* out, frcnn_stream_t stream);
+
+/* ---- utils/metrics.py:136-208 ------------------------------------------------------------ */
+FRCNN_API int frcnn_area(const float* boxes, int64_t n, float* out, frcnn_stream_t stream);
+FRCNN_API int frcnn_intersection_pairwise(const float* b1, int64_t n, const float* b2, int64_t m, float* out,
+                                frcnn_stream_t stream);
+FRCNN_API int frcnn_iou_pairwise(const float* b1, int64_t n, const float* b2, int64_t m, float* out, frcnn_stream_t stream);
+FRCNN_API int frcnn_iou_elementwise(const float* b1, const float* b2, int64_t n, float* out, frcnn_stream_t stream);
+FRCNN_API int frcnn_intersection_elementwise(const float* b1, const float* b2, int64_t n, float* out, frcnn_stream_t stream);
+
+/* ---- utils/post_processing.py:6-63 postprocess_output ---------------------------------------
+ * decode -> to_relative -> drop background column -> tf.image.combined_non_max_suppression
+ * (pad_per_class=False, clip_boxes=True) -> zero-padded outputs.
+ *   regions      [N,4] (regions_batched=0) or [B,N,4] (=1), abs
+ *   pred_scores  [B,N,nc+1]      pred_boxes [B,N,nc,4] encoded
+ *   out_boxes [B,R,4] rel clipped to [0,1]; out_scores [B,R]; out_classes [B,R] int32;
+ *   out_valid [B] int32; out_idx [B,R] int32 region index of each detection, -1 padded (nullable);
+ *   out_exhausted [B] int32 (nullable): 1 if pre_nms_top_n cut the candidate list before
+ *   max_output_size_per_class boxes were kept in some class (result then differs from the reference,
+ *   which has no pre-NMS cap: SURVEY trap T1).  pre_nms_top_n <= 0 means "all" = reference behaviour.
+ * Score ties are visited lower index first; merged detections tie-break by class then rank.
+ * Limits: min(max_per_class, N) <= 4096, nc * min(max_per_class, N) <= 16384, N < 2^22. */
+FRCNN_API size_t frcnn_postprocess_workspace_bytes(int B, int N, int nc, int max_per_class, int max_total);
+FRCNN_API int frcnn_postprocess(float image_height, float image_width, const float* regions, int regions_batched,
+                      const float* pred_scores, const float* pred_boxes, int B, int N, int nc, float score_threshold,
+                      float iou_threshold, int max_per_class, int max_total, int pre_nms_top_n, float* out_boxes,
+                      float* out_scores, int32_t* out_classes, int32_t* out_valid, int32_t* out_idx,
+                      int32_t* out_exhausted, void* workspace, size_t workspace_bytes, frcnn_stream_t stream);
+
+/* Stage 1 of the above (exposed for stage-level parity and profiling): fused decode + to_relative
+ * + background-column drop + score threshold.  boxes_rel [B,nc,N,4] (class-major, unclipped: trap T2),
+ * keys [B,nc,N] uint32 = order-preserving score key, 0 for score <= threshold / NaN. */
+FRCNN_API int frcnn_decode_filter(float image_height, float image_width, const float* regions, int regions_batched,
+                        const float* pred_scores, const float* pred_boxes, int B, int N, int nc,
+                        float score_threshold, float* boxes_rel, uint32_t* keys, frcnn_stream_t stream);
+
+/* Stage 2: segmented greedy NMS in TF order on explicit boxes.  segments = independent (image,class)
+ * problems; boxes [segments,N,4], scores [segments,N]; kept_idx [segments,cap] int32 in keep order
+ * (-1 padded), kept_count [segments] int32, exhausted [segments] int32 (nullable).
+ * cap = min(max_output, N). */
+FRCNN_API size_t frcnn_nms_workspace_bytes(int segments, int N);
+FRCNN_API int frcnn_nms(const float* boxes, const float* scores, int segments, int N, float score_threshold,
+              float iou_threshold, int max_output, int pre_nms_top_n, int32_t* kept_idx, int32_t* kept_count,
+              int32_t* exhausted, void* workspace, size_t workspace_bytes, frcnn_stream_t stream);
+
+/* ---- models/detectors/fast_rcnn_detector.py:133-177 ROIPooling ------------------------------
+ * tf.image.crop_and_resize to (P*k)x(P*k) (bilinear, (H-1) scaling, extrapolation 0) fused with
+ * MaxPool2D(k) (stride k, VALID).  feature_maps [B,Hf,Wf,C] NHWC; rois [B,R,4] rel x1,y1,x2,y2;
+ * out [B,R,P,P,C] (== [B,R,P*P*C] flattened in (py,px,c) order).  P*k <= 32. */
+FRCNN_API int frcnn_roi_pool_forward(const float* feature_maps, int B, int Hf, int Wf, int C, const float* rois, int R,
+                           int pooled_size, int kernel_size, float* out, frcnn_stream_t stream);
+
+/* Gradient w.r.t. feature_maps (models/faster_rcnn.py:73,103 through :168 and :160): MaxPoolGrad to
+ * the first maximum in row-major window order, then CropAndResizeGradImage.  dfeature [B,Hf,Wf,C] is
+ * overwritten (zero-initialised here).  No box gradient (post_processing.py:58 stop_gradient). */
+FRCNN_API int frcnn_roi_pool_backward(const float* feature_maps, int B, int Hf, int Wf, int C, const float* rois, int R,
+                            int pooled_size, int kernel_size, const float* dy, float* dfeature,
+                            frcnn_stream_t stream);
+
+/* ---- utils/training.py:7-77 generate_targets (+ :123-143), batched over images -------------
+ *   gt_labels [B,G,nc+1] one-hot, zero rows = padding; gt_boxes [B,G,4] rel;
+ *   regions [N,4] (regions_batched=0) or [B,N,4], abs.
+ *   target_labels [B,N,nc+1]; target_boxes [B,N,nc,4]; max_iou [B,N], argmax [B,N] int32 (nullable;
+ *   argmax indexes the gt list after padding removal, as the reference's tf.gather sees it).
+ * An image with no gt after padding removal (undefined in the reference) gets max_iou 0,
+ * no forced foreground and zero box targets.  G <= 1024. */
+FRCNN_API size_t frcnn_generate_targets_workspace_bytes(int B, int N);
+FRCNN_API int frcnn_generate_targets(const float* gt_labels, const float* gt_boxes, int B, int G, int nc, const float* regions,
+                           int regions_batched, int N, float image_height, float image_width, float fg_lo,
+                           float fg_hi, float bg_lo, float bg_hi, float* target_labels, float* target_boxes,
+                           float* max_iou, int32_t* argmax, void* workspace, size_t workspace_bytes,
+                           frcnn_stream_t stream);
+
+/* ---- host-buffer pipeline: FasterRCNN.call inference slice, models/faster_rcnn.py:52-55 ------
+ * postprocess_output(rpn) -> ROIPooling on the proposals, taking and returning HOST buffers
+ * (pinned memory recommended).  Owns its device buffers and streams; run() copies inputs host->device,
+ * runs the kernels, copies the results device->host and returns after they have landed. */
+typedef struct frcnn_pipeline frcnn_pipeline_t;
+
+FRCNN_API int frcnn_pipeline_create(frcnn_pipeline_t** out, int B, int Hf, int Wf, int C, int N, int max_total,
+                          int pooled_size, int kernel_size);
+FRCNN_API void frcnn_pipeline_destroy(frcnn_pipeline_t* p);
+/* regions [N,4] abs HOST; pred_scores [B,N,2] HOST; pred_boxes [B,N,1,4] HOST; feature_maps [B,Hf,Wf,C] HOST.
+ * Outputs (HOST): rois [B,R,4], roi_scores [B,R], num_valid [B] int32, pooled [B,R,P,P,C] (nullable: skip copy). */
+FRCNN_API int frcnn_pipeline_run(frcnn_pipeline_t* p, float image_height, float image_width, const float* regions,
+                       const float* pred_scores, const float* pred_boxes, const float* feature_maps,
+                       float score_threshold, float iou_threshold, int pre_nms_top_n, float* rois, float* roi_scores,
+                       int32_t* num_valid, float* pooled);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRCNN_B200_H_ */

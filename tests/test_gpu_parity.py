@@ -1,0 +1,346 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): bit-exact kept-index sets for NMS / top-k given identical fp32 boxes;
+fp32 within 1e-5 relative for decoded boxes, RoI-pool outputs and gradients (the RoI-pool forward and the
+IoU matrix are in fact bit-identical to the oracle, which the tests assert).
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+F = np.float32
+RTOL = 1e-5  # the tolerance north_star states for floating point
+
+
+def dev(x):
+    return torch.as_tensor(np.ascontiguousarray(x)).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+# ------------------------------------------------------------------ elementwise box utils
+def test_boxes_elementwise(det, orc, rng):
+    b = np.sort(rng.uniform(0, 600, (3, 50, 2, 2)).astype(F), axis=2).reshape(3, 50, 4) + F([0, 0, 1, 1])
+    r = np.sort(rng.uniform(0, 600, (50, 2, 2)).astype(F), axis=1).reshape(50, 4) + F([0, 0, 1, 1])
+    t = rng.normal(0, 0.3, (3, 50, 4)).astype(F)
+    np.testing.assert_array_equal(host(det.clip_to_window(dev(b), [10, 20, 500, 300])), orc.clip_to_window(b, [10, 20, 500, 300]))
+    np.testing.assert_allclose(host(det.decode(dev(t), dev(r))), orc.decode(t, r), rtol=RTOL, atol=1e-3)
+    np.testing.assert_allclose(host(det.encode(dev(b), dev(r))), orc.encode(b, r), rtol=RTOL, atol=1e-5)
+    np.testing.assert_array_equal(host(det.to_relative(dev(b), (375, 1242, 3))), orc.to_relative(b, (375, 1242, 3)))
+    np.testing.assert_array_equal(host(det.to_absolute(dev(b / 600), (375, 1242, 3))), orc.to_absolute(b / 600, (375, 1242, 3)))
+    np.testing.assert_array_equal(host(det.decode(dev(np.zeros((50, 4), F)), dev(r))), r)  # decode(0, ref) == ref
+    # broadcast over classes as post_processing.py:40-46 does
+    tt = rng.normal(0, 0.1, (2, 50, 3, 4)).astype(F)
+    np.testing.assert_allclose(host(det.decode(dev(tt), dev(r[:, None, :]))), orc.decode(tt, r[:, None, :]), rtol=RTOL, atol=1e-3)
+    # numpy inputs are uploaded, not computed on the host
+    assert det.decode(t, r).is_cuda
+
+
+def test_anchors_and_valid_indices_exact(det, orc, syn):
+    for name in ("default_b2", "kitti_b8", "dense_b16"):
+        w = syn.WORKLOADS[name]
+        a = det.generate_anchors(w.grid, w.scales, w.aspect_ratios, w.base_anchor_shape)
+        ref = orc.generate_anchors(w.grid, w.scales, w.aspect_ratios, w.base_anchor_shape)
+        np.testing.assert_array_equal(host(a), ref)
+        idx = det.valid_anchor_indices(a, w.image_shape)
+        assert idx.dtype == torch.int64
+        np.testing.assert_array_equal(host(idx), orc.valid_anchor_indices(ref, w.image_shape))
+
+
+def test_rpn_anchors_train_eval_modes(det, orc, syn, rng):
+    w = syn.WORKLOADS["kitti_b8_ref12"]
+    cfg = {"anchors": dict(scales=list(w.scales), aspect_ratios=list(w.aspect_ratios), base_anchor_shape=[256, 256])}
+    ra = det.RPNAnchors(w.image_shape, (None, w.grid[0], w.grid[1], 1024), cfg)
+    scores, deltas = syn.rpn_head_outputs(rng, 2, w.num_anchors)
+    ref = orc.generate_anchors(w.grid, w.scales, w.aspect_ratios, w.base_anchor_shape)
+    ev = ra(dev(scores), dev(deltas), training=False)
+    np.testing.assert_array_equal(host(ev["regions"]), orc.clip_to_window(ref, [0, 0, w.image_shape[1], w.image_shape[0]]))
+    tr = ra(dev(scores), dev(deltas), training=True)
+    idx = orc.valid_anchor_indices(ref, w.image_shape)
+    assert len(idx) == 8768  # N_valid for KITTI with the reference's 12 anchors (T16)
+    np.testing.assert_array_equal(host(tr["regions"]), ref[idx])
+    np.testing.assert_array_equal(host(tr["pred_scores"]), scores[:, idx])
+    np.testing.assert_array_equal(host(tr["pred_boxes"]), deltas[:, idx])
+
+
+def test_iou_bit_exact(det, orc, syn, rng):
+    a = syn.random_rois(rng, 1, 300)[0] * F([1242, 375, 1242, 375])
+    b = np.concatenate([syn.random_rois(rng, 1, 40)[0] * F([1242, 375, 1242, 375]), np.zeros((10, 4), F)])
+    np.testing.assert_array_equal(host(det.iou(dev(a), dev(b), pairwise=True)), orc.iou(a, b, pairwise=True))
+    np.testing.assert_array_equal(host(det.iou(dev(a[:50]), dev(b), pairwise=False)), orc.iou(a[:50], b))
+    np.testing.assert_array_equal(host(det.intersection(dev(a), dev(b), pairwise=True)), orc.intersection(a, b, pairwise=True))
+    np.testing.assert_array_equal(host(det.intersection(dev(a[:50]), dev(b))), orc.intersection(a[:50], b))
+    np.testing.assert_array_equal(host(det.area(dev(a))), orc.area(a))
+
+
+# ------------------------------------------------------------------ NMS stage: bit-exact kept indices
+def _decoded(orc, syn, wname, batch, seed):
+    w = syn.WORKLOADS[wname]
+    rng = np.random.default_rng(seed)
+    anchors = orc.clip_to_window(orc.generate_anchors(w.grid, w.scales, w.aspect_ratios, w.base_anchor_shape),
+                                 [0, 0, w.image_shape[1], w.image_shape[0]])
+    scores, deltas = syn.rpn_head_outputs(rng, batch, w.num_anchors)
+    boxes = orc.to_relative(orc.decode(deltas[:, :, 0], anchors), w.image_shape)
+    return w, anchors, scores, deltas, boxes
+
+
+@pytest.mark.parametrize("wname,batch,top_n,cap", [("kitti_b8", 4, None, 300), ("kitti_b8", 2, 2000, 300),
+                                                   ("kitti_b8_ref12", 2, None, 300), ("default_b2", 1, None, 300),
+                                                   ("dense_b16", 1, 12000, 1000), ("kitti_b8", 1, 100, 300),
+                                                   ("kitti_b8", 1, None, 2000)])
+def test_nms_kept_indices_bit_exact(det, orc, syn, wname, batch, top_n, cap):
+    w, anchors, scores, deltas, boxes = _decoded(orc, syn, wname, batch, 7)
+    kept, cnt, exh = det.non_max_suppression(dev(boxes), dev(scores[..., 1]), 0.0, 0.7, cap, top_n)
+    kept, cnt, exh = host(kept), host(cnt), host(exh)
+    for b in range(batch):
+        ref = orc.nms(boxes[b], scores[b, :, 1], 0.0, 0.7, cap, top_n)
+        assert cnt[b] == len(ref)
+        np.testing.assert_array_equal(kept[b, :cnt[b]], ref)
+        assert (kept[b, cnt[b]:] == -1).all()
+        if top_n is not None and len(ref) < cap:
+            assert exh[b] == 1  # the cap cut the list short: flagged (T1)
+        if top_n is None:
+            assert exh[b] == 0
+
+
+def test_nms_heavy_suppression_many_chunks(det, orc, rng):
+    """Spatially clustered boxes: most candidates are suppressed, so the greedy loop walks many 512-candidate chunks."""
+    n = 20000
+    ctr = rng.uniform(0.1, 0.9, (40, 2))[rng.integers(0, 40, n)] + rng.normal(0, 0.01, (n, 2))
+    wh = rng.uniform(0.08, 0.12, (n, 2))
+    boxes = np.concatenate([ctr - wh / 2, ctr + wh / 2], -1).astype(F)
+    scores = (rng.permutation(n).astype(F) + 1) / (n + 1)
+    for thr, cap in ((0.5, 300), (0.3, 1000), (0.7, 50)):
+        kept, cnt, _ = det.non_max_suppression(dev(boxes), dev(scores), 0.0, thr, cap)
+        ref = orc.nms(boxes, scores, 0.0, thr, cap)
+        np.testing.assert_array_equal(host(kept)[:int(cnt)], ref)
+
+
+def test_nms_score_ties_lower_index_first(det, orc, rng):
+    n = 3000
+    xy = rng.uniform(0, 1, (n, 2))
+    boxes = np.concatenate([xy, xy + rng.uniform(0.02, 0.2, (n, 2))], -1).astype(F)
+    for scores in (np.full(n, 0.5, F), (rng.integers(0, 7, n) / 8 + 0.0625).astype(F),
+                   np.repeat(rng.uniform(0.1, 0.9, n // 600).astype(F), 600)):
+        kept, cnt, _ = det.non_max_suppression(dev(boxes), dev(scores), 0.0, 0.5, 700)
+        np.testing.assert_array_equal(host(kept)[:int(cnt)], orc.nms(boxes, scores, 0.0, 0.5, 700))
+        kept, cnt, _ = det.non_max_suppression(dev(boxes), dev(scores), 0.0, 0.5, 700, 900)
+        np.testing.assert_array_equal(host(kept)[:int(cnt)], orc.nms(boxes, scores, 0.0, 0.5, 700, 900))
+
+
+def test_nms_edge_cases(det, orc, rng):
+    boxes = np.array([[0, 0, 10, 10], [1, 1, 11, 11], [20, 20, 30, 30]], F)
+    scores = np.array([0.9, 0.8, 0.7], F)
+    for args in ((0.0, 0.5, 10), (0.0, 0.7, 10), (0.0, 0.5, 1), (0.75, 0.7, 10), (0.7, 0.7, 10), (0.95, 0.5, 10), (0.0, 0.5, 0)):
+        kept, cnt, _ = det.non_max_suppression(dev(boxes), dev(scores), *args)
+        np.testing.assert_array_equal(host(kept)[:int(cnt)], orc.nms(boxes, scores, *args))
+    # IoU exactly at the threshold is kept (strict >), degenerate and flipped boxes, negative / NaN scores
+    b2 = np.array([[0, 0, 2, 2], [0, 0, 2, 1], [5, 5, 5, 9], [10, 10, 0, 0], [0, 0, 10, 10]], F)
+    s2 = np.array([0.9, 0.8, 0.7, 0.6, np.nan], F)
+    for thr in (0.5, 0.49):
+        kept, cnt, _ = det.non_max_suppression(dev(b2), dev(s2), 0.0, thr, 10)
+        np.testing.assert_array_equal(host(kept)[:int(cnt)], orc.nms(b2, s2, 0.0, thr, 10))
+    s3 = np.array([-0.5, -0.2, -0.9, 0.1, -0.3], F)
+    kept, cnt, _ = det.non_max_suppression(dev(b2), dev(s3), -1.0, 0.5, 10)
+    np.testing.assert_array_equal(host(kept)[:int(cnt)], orc.nms(b2, s3, -1.0, 0.5, 10))
+
+
+# ------------------------------------------------------------------ postprocess_output end to end
+def _check_post(det, orc, image_shape, regions, scores, deltas, kw, top_n=None):
+    out = det.postprocess_output(image_shape, dev(regions), dev(scores), dev(deltas), **kw, pre_nms_top_n=top_n, return_extra=True)
+    ref = orc.postprocess_output(image_shape, regions, scores, deltas, **kw, pre_nms_top_n=top_n, return_extra=True)
+    assert out["pred_classes"].dtype == torch.int32 and out["num_valid_detections"].dtype == torch.int32  # T14
+    np.testing.assert_array_equal(host(out["num_valid_detections"]), ref["num_valid_detections"])
+    np.testing.assert_array_equal(host(out["kept_indices"]), ref["kept_indices"])  # bit-exact index sets
+    np.testing.assert_array_equal(host(out["pred_classes"]), ref["pred_classes"])
+    np.testing.assert_array_equal(host(out["pred_scores"]), ref["pred_scores"])
+    np.testing.assert_allclose(host(out["pred_boxes"]), ref["pred_boxes"], rtol=RTOL, atol=1e-6)
+    return out, ref
+
+
+@pytest.mark.parametrize("wname,batch,top_n", [("kitti_b8", 8, None), ("kitti_b8", 8, 2000), ("kitti_b8_ref12", 3, None),
+                                               ("default_b2", 2, None)])
+def test_postprocess_rpn_form(det, orc, syn, wname, batch, top_n):
+    w, anchors, scores, deltas, _ = _decoded(orc, syn, wname, batch, 20241)
+    out, ref = _check_post(det, orc, w.image_shape, anchors, scores, deltas, w.nms_kwargs(), top_n)
+    pb = host(out["pred_boxes"])
+    assert pb.min() >= 0 and pb.max() <= 1  # clipped on output only (T2)
+    assert (host(out["num_valid_detections"]) == 300).all()
+
+
+def test_postprocess_decode_stage_and_unclipped_iou(det, orc, syn):
+    w, anchors, scores, deltas, boxes = _decoded(orc, syn, "kitti_b8", 2, 5)
+    brel, keys = det.decode_filter(w.image_shape, dev(anchors), dev(scores), dev(deltas), 0.0)
+    brel = host(brel)[:, 0]
+    np.testing.assert_allclose(brel, boxes, rtol=RTOL, atol=1e-6)
+    assert brel.min() < 0 or brel.max() > 1  # unclipped boxes feed NMS (T2)
+    # given the GPU's own decoded boxes, the kept set must be bit-exact
+    out = det.postprocess_output(w.image_shape, dev(anchors), dev(scores), dev(deltas), **w.nms_kwargs(), return_extra=True)
+    for b in range(2):
+        ref = orc.nms(brel[b], scores[b, :, 1], 0.0, 0.7, 300)
+        np.testing.assert_array_equal(host(out["kept_indices"])[b, :len(ref)], ref)
+
+
+def test_postprocess_rcnn_form_multiclass(det, orc, syn, rng):
+    B, R, nc = 4, 300, 7
+    image_shape = (375, 1242, 3)
+    rois = syn.random_rois(rng, B, R) * F([1242, 375, 1242, 375])
+    logits = rng.normal(0, 1.5, (B, R, nc + 1)).astype(F)
+    sc = (np.exp(logits) / np.exp(logits).sum(-1, keepdims=True)).astype(F)
+    dl = rng.normal(0, 0.1, (B, R, nc, 4)).astype(F)
+    kw = dict(score_threshold=0.0, iou_threshold=0.6, max_output_size_per_class=100, max_total_size=300)
+    out, ref = _check_post(det, orc, image_shape, rois, sc, dl, kw)
+    assert (host(out["num_valid_detections"]) == 300).all()
+    kw2 = dict(score_threshold=0.3, iou_threshold=0.5, max_output_size_per_class=10, max_total_size=300)
+    out, ref = _check_post(det, orc, image_shape, rois, sc, dl, kw2)  # fewer than max_total valid -> zero padding
+    nv = host(out["num_valid_detections"])
+    assert (nv < 300).all()
+    assert (host(out["pred_boxes"])[0, nv[0]:] == 0).all() and (host(out["pred_scores"])[0, nv[0]:] == 0).all()
+
+
+def test_postprocess_small_and_empty(det, orc, syn, rng):
+    anchors = orc.generate_anchors((3, 4), [0.5, 1.0], [1.0], [64, 64])
+    scores, deltas = syn.rpn_head_outputs(rng, 2, anchors.shape[0])
+    kw = dict(score_threshold=0.0, iou_threshold=0.7, max_output_size_per_class=300, max_total_size=300)
+    _check_post(det, orc, (48, 64, 3), anchors, scores, deltas, kw)  # N < max_total: cap = N (T17)
+    kw["score_threshold"] = 2.0  # nothing passes the threshold
+    out, _ = _check_post(det, orc, (48, 64, 3), anchors, scores, deltas, kw)
+    assert (host(out["num_valid_detections"]) == 0).all() and (host(out["pred_boxes"]) == 0).all()
+    with pytest.raises(ValueError):
+        det.postprocess_output((48, 64, 3), dev(anchors), dev(scores[:, :-1]), dev(deltas), **kw)
+
+
+# ------------------------------------------------------------------ RoI pooling
+@pytest.mark.parametrize("grid,C,R,relu", [((24, 78), 1024, 40, True), ((6, 9), 64, 7, False), ((38, 125), 256, 12, True),
+                                           ((5, 5), 6, 4, True)])
+def test_roi_pool_forward_bit_exact(det, orc, syn, rng, grid, C, R, relu):
+    f = syn.feature_maps(rng, 2, grid, C, relu=relu)
+    rois = syn.random_rois(rng, 2, R, num_valid=[R - 2, R])  # padded [0,0,0,0] rows still pooled (T7)
+    rois[1, 0] = [0.25, 0.1, 1.0, 1.0]  # y2 = x2 = 1.0 exactly (T6)
+    out = det.roi_pool_forward(dev(f), dev(rois), 7, 2)
+    np.testing.assert_array_equal(host(out), orc.roi_pool_forward(f, rois, 7, 2))
+    pooled = det.ROIPooling(pooled_size=7, kernel_size=2)(dev(f), dev(rois), True, True)
+    assert tuple(pooled.shape) == (2, R, 49 * C)
+    np.testing.assert_array_equal(host(pooled).reshape(2, R, 7, 7, C), host(out))
+    assert tuple(det.ROIPooling(7, 2)(dev(f), dev(rois)).shape) == (2 * R, 7, 7, C)
+
+
+def test_roi_pool_other_window_sizes_and_out_of_range(det, orc, syn, rng):
+    f = syn.feature_maps(rng, 1, (9, 11), 8, relu=False)
+    rois = np.array([[[-0.2, -0.1, 0.6, 0.7], [0.3, 0.4, 1.3, 1.2], [0.5, 0.5, 0.5, 0.5], [0.9, 0.8, 0.1, 0.2]]], F)
+    for P, k in ((7, 2), (4, 1), (3, 3), (1, 2), (1, 1), (8, 4)):
+        np.testing.assert_array_equal(host(det.roi_pool_forward(dev(f), dev(rois), P, k)), orc.roi_pool_forward(f, rois, P, k))
+
+
+@pytest.mark.parametrize("grid,C,R,relu", [((24, 78), 256, 30, True), ((6, 9), 64, 9, False), ((7, 5), 3, 5, True)])
+def test_roi_pool_backward(det, orc, syn, rng, grid, C, R, relu):
+    f = syn.feature_maps(rng, 2, grid, C, relu=relu)
+    rois = syn.random_rois(rng, 2, R, num_valid=[R - 3, R])
+    dy = rng.standard_normal((2, R, 7, 7, C)).astype(F)
+    ref = orc.roi_pool_backward(f, rois, dy, 7, 2)
+    got = host(det.roi_pool_backward(dev(f), dev(rois), dev(dy), 7, 2))
+    # summation order differs (atomics vs the oracle's sequential adds): 1e-5 relative with an absolute floor
+    np.testing.assert_allclose(got, ref, rtol=RTOL, atol=RTOL * np.abs(ref).max())
+    # autograd route (what the train step uses) gives the same gradient; no gradient flows to the boxes
+    ft = dev(f).requires_grad_(True)
+    rt = dev(rois).requires_grad_(True)
+    det.ROIPooling(7, 2)(ft, rt, True, True).backward(dev(dy).reshape(2, R, -1))
+    np.testing.assert_allclose(host(ft.grad), ref, rtol=RTOL, atol=RTOL * np.abs(ref).max())
+    assert rt.grad is None
+
+
+# ------------------------------------------------------------------ generate_targets
+def test_generate_targets_rpn_and_rcnn(det, orc, syn, rng):
+    w = syn.WORKLOADS["kitti_b8_ref12"]
+    anchors = orc.generate_anchors(w.grid, w.scales, w.aspect_ratios, w.base_anchor_shape)
+    regions = anchors[orc.valid_anchor_indices(anchors, w.image_shape)]
+    B = 5
+    gl, gb = syn.ground_truth(rng, B, allow_empty=False)
+    obj = orc.rpn_objectness_labels(gl)
+    np.testing.assert_array_equal(host(det.rpn_objectness_labels(dev(gl))), obj)
+    tl, tb, mi, am = det.generate_targets_batched(dev(obj), dev(gb), dev(regions), w.image_shape, [0.7, 1.0], [0.0, 0.3], return_extra=True)
+    for b in range(B):
+        rl, rb, rmi, ram = orc.generate_targets(obj[b], gb[b], regions, w.image_shape, [0.7, 1.0], [0.0, 0.3], return_extra=True)
+        np.testing.assert_array_equal(host(mi)[b], rmi)  # IoU is bit-exact
+        np.testing.assert_array_equal(host(am)[b], ram)
+        np.testing.assert_array_equal(host(tl)[b], rl)
+        np.testing.assert_allclose(host(tb)[b], rb, rtol=RTOL, atol=1e-6)
+        assert host(tl)[b][:, 1].sum() >= 1  # at least one foreground (forced, T12)
+    # RCNN form: per-image regions [B,300,4], 7 classes, padding really removed
+    rois = syn.random_rois(rng, B, 300) * F([w.image_shape[1], w.image_shape[0]] * 2)
+    tl, tb = det.generate_targets_batched(dev(gl), dev(gb), dev(rois), w.image_shape, [0.5, 1.0], [0.0, 0.5])
+    for b in range(B):
+        rl, rb = orc.generate_targets(gl[b], gb[b], rois[b], w.image_shape, [0.5, 1.0], [0.0, 0.5])
+        np.testing.assert_array_equal(host(tl)[b], rl)
+        np.testing.assert_allclose(host(tb)[b], rb, rtol=RTOL, atol=1e-6)
+    # single-image signature of the reference
+    a, c = det.generate_targets(dev(gl[0]), dev(gb[0]), dev(rois[0]), w.image_shape, [0.5, 1.0], [0.0, 0.5])
+    np.testing.assert_array_equal(host(a), host(tl)[0])
+
+
+def test_generate_targets_kat_and_no_gt(det, orc):
+    image_shape = (100, 200, 3)
+    regions = np.array([[0, 0, 50, 50], [0, 0, 50, 40], [0, 0, 50, 20], [100, 50, 150, 100], [0, 0, 50, 50]], F)
+    gb = np.zeros((4, 4), F)
+    gb[0] = [0, 0, 0.25, 0.5]
+    gl = np.zeros((4, 3), F)
+    gl[0, 2] = 1
+    tl, tb = det.generate_targets(dev(gl), dev(gb), dev(regions), image_shape, [0.7, 1.0], [0.0, 0.3])
+    np.testing.assert_array_equal(host(tl), [[0, 0, 1], [0, 0, 1], [0, 0, 0], [1, 0, 0], [0, 0, 0]])  # T12
+    rl, rb = orc.generate_targets(gl, gb, regions, image_shape, [0.7, 1.0], [0.0, 0.3])
+    np.testing.assert_allclose(host(tb), rb, rtol=RTOL, atol=1e-7)
+    tl, tb = det.generate_targets(dev(np.zeros((4, 3), F)), dev(gb), dev(regions), image_shape, [0.5, 1.0], [0.0, 0.5])
+    np.testing.assert_array_equal(host(tl), np.tile([1, 0, 0], (5, 1)))  # T13: documented choice
+    np.testing.assert_array_equal(host(tb), 0)
+
+
+def test_get_sample_indices_rule(det, rng):
+    tl = np.zeros((1000, 2), F)
+    tl[:40, 1] = 1
+    tl[100:900, 0] = 1
+    g = torch.Generator(device="cuda").manual_seed(0)
+    idx = host(det.get_sample_indices(dev(tl), 256, 0.5, generator=g))
+    assert idx.shape == (256,) and idx.dtype == np.int64  # T14
+    assert (idx[:40] < 40).all() and len(set(idx[:40].tolist())) == 40  # all 40 foregrounds, no repeats
+    assert ((idx[40:] >= 100) & (idx[40:] < 900)).all()
+
+
+# ------------------------------------------------------------------ host-buffer pipeline == device API
+def test_host_pipeline_matches_device_api(det, orc, syn):
+    w, anchors, scores, deltas, _ = _decoded(orc, syn, "kitti_b8", 2, 11)
+    f = syn.feature_maps(np.random.default_rng(3), 2, w.grid, 128)
+    pipe = det.ProposalRoIPipeline(w.image_shape, 2, w.grid, 128, w.num_anchors, 0.0, 0.7, 300, pre_nms_top_n=2000)
+    rois, rs, nv, pooled = pipe(anchors, scores, deltas, f)
+    out = det.postprocess_output(w.image_shape, dev(anchors), dev(scores), dev(deltas), **w.nms_kwargs(), pre_nms_top_n=2000)
+    np.testing.assert_array_equal(rois.numpy(), host(out["pred_boxes"]))
+    np.testing.assert_array_equal(rs.numpy(), host(out["pred_scores"]))
+    np.testing.assert_array_equal(nv.numpy(), host(out["num_valid_detections"]))
+    np.testing.assert_array_equal(pooled.numpy(), host(det.roi_pool_forward(dev(f), out["pred_boxes"], 7, 2)))
+    np.testing.assert_array_equal(pooled.numpy(), orc.roi_pool_forward(f, rois.numpy(), 7, 2))
+    pipe.close()
+
+
+# ------------------------------------------------------------------ full-size properties (BASELINE sizes)
+def test_full_size_properties_kitti_b8(det, orc, syn):
+    w, anchors, scores, deltas, boxes = _decoded(orc, syn, "kitti_b8", 8, 20241)
+    out = det.postprocess_output(w.image_shape, dev(anchors), dev(scores), dev(deltas), **w.nms_kwargs(), return_extra=True)
+    idx, sc = host(out["kept_indices"]), host(out["pred_scores"])
+    for b in range(8):
+        assert len(set(idx[b].tolist())) == 300 and (np.diff(sc[b]) < 0).all()  # distinct, strictly descending
+        kb = boxes[b][idx[b]]
+        iou = np.array([[orc.tf_nms_iou(kb[i], kb[j]) for j in range(0, 300, 7)] for i in range(0, 300, 5)])
+        assert (iou[iou < 0.999] <= F(0.7)).all()  # independent set at the threshold
+    f = syn.feature_maps(np.random.default_rng(1), 8, w.grid, 1024)
+    pooled = det.roi_pool_forward(dev(f), out["pred_boxes"], 7, 2)
+    assert tuple(pooled.shape) == (8, 300, 7, 7, 1024)
+    assert float(pooled.min()) >= 0.0 and float(pooled.max()) <= float(f.max())  # max of convex combinations
+    const = det.roi_pool_forward(torch.full((8, 24, 78, 1024), 2.5, device="cuda"), out["pred_boxes"], 7, 2)
+    assert bool((const == 2.5).all())  # RoI pool of a constant map is the constant
+    # idempotence / determinism of the whole forward
+    again = det.postprocess_output(w.image_shape, dev(anchors), dev(scores), dev(deltas), **w.nms_kwargs(), return_extra=True)
+    assert torch.equal(again["kept_indices"], out["kept_indices"]) and torch.equal(again["pred_boxes"], out["pred_boxes"])
+    # bit-exact pooled features for one image against the oracle at full width
+    np.testing.assert_array_equal(host(pooled[3]), orc.roi_pool_forward(f[3:4], host(out["pred_boxes"])[3:4], 7, 2)[0])
