@@ -22,7 +22,7 @@ from . import _lib
 
 _lib.load()  # fail loudly at import if the CUDA library has not been built
 
-from . import synthetic  # noqa: E402
+from . import engine, sharding, synthetic  # noqa: E402
 from .models.detectors.fast_rcnn_detector import ROIPooling, roi_pool_backward, roi_pool_forward  # noqa: E402
 from .models.detectors.rpn_detector import (RPNAnchors, generate_anchors,  # noqa: E402
                                             remove_invalid_anchors_and_predictions, valid_anchor_indices)

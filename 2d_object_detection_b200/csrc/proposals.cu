@@ -95,12 +95,16 @@ struct NmsShared {
     unsigned int alive32[kChunk / 32];
 };
 
+constexpr size_t kNmsSharedBytes = (sizeof(NmsShared) + 15) / 16 * 16;
+
 __global__ void __launch_bounds__(kNmsThreads, 1)
     nms_select_kernel(const float4* __restrict__ boxes, const uint32_t* __restrict__ keys, int N, int cap, int top_n,
                       float iou_thr, int32_t* __restrict__ kept_idx, int32_t* __restrict__ kept_count,
                       int32_t* __restrict__ exhausted) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long* comp = reinterpret_cast<unsigned long long*>(smem_raw);             // [kChunk]
+    // 8-byte items first, then 16-byte boxes, then 4-byte arrays: every sub-array stays naturally aligned for any cap
+    NmsShared* S = reinterpret_cast<NmsShared*>(smem_raw);
+    unsigned long long* comp = reinterpret_cast<unsigned long long*>(smem_raw + kNmsSharedBytes);  // [kChunk]
     unsigned long long* mask = comp + kChunk;                                              // [kChunk*kChunkWords]
     float4* cbox = reinterpret_cast<float4*>(mask + kChunk * kChunkWords);                  // [kChunk]
     float4* kbox = cbox + kChunk;                                                          // [cap]
@@ -108,7 +112,6 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
     float* karea = carea + kChunk;                                                         // [cap]
     unsigned int* hist = reinterpret_cast<unsigned int*>(karea + cap);                      // [kBins]
     int* alive = reinterpret_cast<int*>(hist + kBins);                                      // [kChunk]
-    NmsShared* S = reinterpret_cast<NmsShared*>(alive + kChunk);
 
     const int seg = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -393,7 +396,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
 static size_t nms_smem_bytes(int cap) {
     return sizeof(unsigned long long) * (kChunk + kChunk * kChunkWords) + sizeof(float4) * (kChunk + (size_t)cap) +
            sizeof(float) * (kChunk + (size_t)cap) + sizeof(unsigned int) * kBins + sizeof(int) * kChunk +
-           sizeof(NmsShared) + 16;
+           kNmsSharedBytes + 16;
 }
 
 // ------------------------------------------------------------------------------------------------
