@@ -119,6 +119,176 @@ __global__ void __launch_bounds__(kRoiThreads)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fast forward path for kernel_size == 2 (the reference configuration), float4 channels.
+// A thread owns one float4 of channels and walks one bin-row (two crop rows) from left to right.
+// The four feature rows it touches (top/bottom of both crop rows) and the current left/right
+// feature columns live in registers: when the next sample falls in the same cell nothing is loaded,
+// when it moves one cell right the right column is shifted into the left one and only one new column
+// is fetched.  Rows shared between the two crop rows (the common case: crop step < 1 feature cell)
+// are fetched and x-interpolated once.  All branch conditions depend on the RoI only, so they are
+// uniform over the CTA.  The arithmetic per sample is unchanged (bit-identical to the generic kernel).
+// ------------------------------------------------------------------------------------------------
+struct AxisY {             // per crop row: element offsets (in float4) of the two feature rows
+    int lo[kMaxCrop];
+    int hi[kMaxCrop];
+    float lerp[kMaxCrop];
+    int valid[kMaxCrop];
+};
+struct AxisX {             // per crop column: feature cell (left column index, -1 = outside the map) and x_lerp
+    int cell[kMaxCrop];
+    float lerp[kMaxCrop];
+};
+
+__device__ __forceinline__ float4 vmax4(const float4& a, const float4& b) {
+    return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+}
+
+// Walk one bin-row (two crop rows) left to right, cell by cell.
+// NR = number of distinct feature rows under the two crop rows:
+//   2: both crop rows in the same cell        (rows t, b;          s0 = y(X0,X1), s1 = y(X0,X1))
+//   3: second crop row one cell further down  (rows t0, b0=t1, b1;   s0 = y(X0,X1), s1 = y(X1,X2))
+//   4: anything else, including crop rows outside the map (kCheckY) -- no sharing assumed.
+// VPT = float4 channel vectors per thread (thread t owns vectors t, t+T, ...: each warp access stays a
+// contiguous 512 B); VPT = 2 halves the per-sample index/branch overhead relative to the fp32 work.
+// Two register column sets A and B alternate as left/right neighbour: moving one cell to the right loads
+// ONE new column into the set that held the old left column and swaps roles (two copies of the sample
+// code, no register shuffling); every feature value is loaded exactly once per bin-row.  The right
+// neighbour of an integer position is taken as column c+1 instead of TF's ceil() == c: its weight is
+// x_lerp == 0, so the interpolated value is identical.  All branches are CTA-uniform.
+template <int NR, bool kCheckY, int VPT, int T>
+__device__ __forceinline__ void walk_bin_row(const float4* __restrict__ f, const int (&roff)[4], float yl0, float yl1,
+                                             bool yv0, bool yv1, const AxisX& ax, int S, int last_col, int CV,
+                                             float4* __restrict__ orow) {
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* fr[NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) fr[k] = f + roff[k];
+    float4 A[NR][VPT], B[NR][VPT];
+    float4 best[VPT];
+    float4* optr = orow;
+    auto load_col = [&](float4 (&dst)[NR][VPT], int col) {
+        const int off = min(col, last_col) * CV;
+#pragma unroll
+        for (int k = 0; k < NR; ++k) {
+            const float4* p = fr[k] + off;
+#pragma unroll
+            for (int v = 0; v < VPT; ++v) dst[k][v] = __ldg(p + v * T);
+        }
+    };
+    auto emit_zero = [&](int sx) {
+        if (sx & 1) {
+#pragma unroll
+            for (int v = 0; v < VPT; ++v) st_cs_f4(optr + v * T, vmax4(best[v], zero));
+            optr += CV;
+        } else {
+#pragma unroll
+            for (int v = 0; v < VPT; ++v) best[v] = zero;
+        }
+    };
+    auto emit = [&](int sx, const float4 (&L)[NR][VPT], const float4 (&Rt)[NR][VPT]) {
+        const float xl = ax.lerp[sx];
+        float4 m[VPT];
+#pragma unroll
+        for (int v = 0; v < VPT; ++v) {
+            float4 X[NR];
+#pragma unroll
+            for (int k = 0; k < NR; ++k) X[k] = lerpv(L[k][v], Rt[k][v], xl);
+            float4 s0 = lerpv(X[0], X[1], yl0);
+            float4 s1 = NR == 2 ? lerpv(X[0], X[1], yl1) : NR == 3 ? lerpv(X[1], X[2], yl1) : lerpv(X[NR - 2], X[NR - 1], yl1);
+            if (kCheckY) {
+                if (!yv0) s0 = zero;  // extrapolation_value = 0 for a crop row outside the map
+                if (!yv1) s1 = zero;
+            }
+            m[v] = vmax4(s0, s1);
+        }
+        if (sx & 1) {
+#pragma unroll
+            for (int v = 0; v < VPT; ++v) st_cs_f4(optr + v * T, vmax4(best[v], m[v]));
+            optr += CV;
+        } else {
+#pragma unroll
+            for (int v = 0; v < VPT; ++v) best[v] = m[v];
+        }
+    };
+    int sx = 0;
+    while (sx < S) {
+        int c = ax.cell[sx];
+        if (c < 0) {  // crop column outside the map
+            emit_zero(sx);
+            ++sx;
+            continue;
+        }
+        load_col(A, c);
+        load_col(B, c + 1);
+        for (;;) {
+            do {  // left = A, right = B
+                emit(sx, A, B);
+                ++sx;
+            } while (sx < S && ax.cell[sx] == c);
+            if (sx >= S || ax.cell[sx] != c + 1) break;
+            ++c;
+            load_col(A, c + 1);
+            do {  // left = B, right = A
+                emit(sx, B, A);
+                ++sx;
+            } while (sx < S && ax.cell[sx] == c);
+            if (sx >= S || ax.cell[sx] != c + 1) break;
+            ++c;
+            load_col(B, c + 1);
+        }
+    }
+}
+
+// grid (R, B); T threads; each thread owns VPT float4 channel vectors per pass over the channels.
+template <int VPT, int T>
+__global__ void __launch_bounds__(T, 512 / T)
+    roi_pool_fwd_k2_kernel(const float4* __restrict__ feat, int Hf, int Wf, int CV, const float4* __restrict__ rois, int R,
+                           int P, float4* __restrict__ out) {
+    __shared__ AxisTab ty, tx;
+    __shared__ AxisY ay;
+    __shared__ AxisX ax;
+    const int r = blockIdx.x, b = blockIdx.y;
+    const int S = 2 * P;
+    const float4 roi = rois[(size_t)b * R + r];
+    if (threadIdx.x < S) {
+        const int i = threadIdx.x;
+        axis_sample(roi.y, roi.w, Hf, S, i, ty);
+        ay.lo[i] = ty.lo[i] * Wf * CV;
+        ay.hi[i] = ty.hi[i] * Wf * CV;
+        ay.lerp[i] = ty.lerp[i];
+        ay.valid[i] = ty.valid[i];
+    } else if (threadIdx.x >= 32 && threadIdx.x < 32 + S) {
+        const int i = threadIdx.x - 32;
+        axis_sample(roi.x, roi.z, Wf, S, i, tx);
+        ax.cell[i] = tx.valid[i] ? tx.lo[i] : -1;
+        ax.lerp[i] = tx.lerp[i];
+    }
+    __syncthreads();
+    const float4* fb = feat + (size_t)b * Hf * Wf * CV;
+    float4* ob = out + ((size_t)b * R + r) * P * P * CV;
+    for (int cv = threadIdx.x; cv < CV; cv += T * VPT) {  // host guarantees CV % (T*VPT) == 0 when VPT > 1
+        const float4* f = fb + cv;
+        for (int py = 0; py < P; ++py) {
+            const int sy0 = 2 * py, sy1 = sy0 + 1;
+            const int t0 = ay.lo[sy0], b0 = ay.hi[sy0], t1 = ay.lo[sy1], b1 = ay.hi[sy1];
+            const float yl0 = ay.lerp[sy0], yl1 = ay.lerp[sy1];
+            const bool yv0 = ay.valid[sy0] != 0, yv1 = ay.valid[sy1] != 0;
+            float4* orow = ob + (size_t)py * P * CV + cv;
+            if (yv0 && yv1 && t1 == t0 && b1 == b0) {
+                const int roff[4] = {t0, b0, 0, 0};
+                walk_bin_row<2, false, VPT, T>(f, roff, yl0, yl1, true, true, ax, S, Wf - 1, CV, orow);
+            } else if (yv0 && yv1 && t1 == b0) {
+                const int roff[4] = {t0, b0, b1, 0};
+                walk_bin_row<3, false, VPT, T>(f, roff, yl0, yl1, true, true, ax, S, Wf - 1, CV, orow);
+            } else {
+                const int roff[4] = {t0, b0, t1, b1};
+                walk_bin_row<4, true, VPT, T>(f, roff, yl0, yl1, yv0, yv1, ax, S, Wf - 1, CV, orow);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Backward.  Each thread re-derives the arg-max sample of its bins from the feature map (no saved
 // state), then scatters the four bilinear weights with 16-byte vector reductions (red.global.add.v4.f32).
 // Channels whose arg-max is a different sample of the window contribute an exact 0 to that reduction.
@@ -218,7 +388,18 @@ int frcnn_roi_pool_forward(const float* feat, int B, int Hf, int Wf, int C, cons
     FRCNN_REQUIRE(B <= 65535, FRCNN_ELIMIT, "roi_pool_forward: B > 65535");
     if (R == 0) return 0;
     const dim3 grid(R, B);
-    if (C % 4 == 0)
+    if (C % 4 == 0 && k == 2 && (int64_t)Hf * Wf * (C / 4) < (1ll << 31)) {
+        const int cv = C / 4;
+        if (cv % 256 == 0)
+            roi_pool_fwd_k2_kernel<2, 128><<<grid, 128, 0, as_stream(stream)>>>((const float4*)feat, Hf, Wf, cv,
+                                                                                (const float4*)rois, R, P, (float4*)out);
+        else if (cv > 64)
+            roi_pool_fwd_k2_kernel<1, 128><<<grid, 128, 0, as_stream(stream)>>>((const float4*)feat, Hf, Wf, cv,
+                                                                                (const float4*)rois, R, P, (float4*)out);
+        else
+            roi_pool_fwd_k2_kernel<1, 64><<<grid, 64, 0, as_stream(stream)>>>((const float4*)feat, Hf, Wf, cv,
+                                                                              (const float4*)rois, R, P, (float4*)out);
+    } else if (C % 4 == 0)
         roi_pool_fwd_kernel<float4><<<grid, kRoiThreads, 0, as_stream(stream)>>>((const float4*)feat, Hf, Wf, C / 4,
                                                                                   (const float4*)rois, R, P, k,
                                                                                   (float4*)out);
