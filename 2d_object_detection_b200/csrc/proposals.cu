@@ -66,7 +66,6 @@ __global__ void score_keys_kernel(const float* __restrict__ scores, int64_t n, f
 // ------------------------------------------------------------------------------------------------
 constexpr int kNmsThreads = 1024;
 constexpr int kChunk = 512;          // candidates ordered + resolved per iteration
-constexpr int kChunkWords = kChunk / 64;
 constexpr int kBins = 2048;          // 11-bit radix digits
 
 // TF CombinedNMS IOU on corner-normalised boxes with precomputed areas; returns iou > thr.
@@ -90,13 +89,24 @@ struct NmsShared {
     unsigned long long hi;        // exclusive upper bound of unvisited composites
     unsigned long long pfx, pmask;
     unsigned long long thresh;    // chunk = eligible composites >= thresh
-    int need, want, m, kept, budget, remaining, stop, select_done;
+    int need, want_max, want_min, expect, kept, budget, remaining, stop, select_done;
     unsigned int cnt;
-    unsigned int alive32[kChunk / 32];
+    unsigned int dead[2];         // per 64-block: candidates suppressed by already kept boxes
+    unsigned int diag[128];       // per 64-block: 64x64 suppression bits among the block (row r: words 2r, 2r+1)
 };
 
 constexpr size_t kNmsSharedBytes = (sizeof(NmsShared) + 15) / 16 * 16;
 
+// One persistent CTA per (image, class) segment.
+//   loop over chunks of the candidate list in (score desc, index asc) order:
+//     SELECT   11-bit MSD radix select over the 64-bit composite (score key, ~index) finds a threshold that cuts
+//              off the next <= 512 unvisited candidates; whole histogram bins are accepted as soon as they give
+//              at least half a chunk, so unique scores need two histogram sweeps over the keys.
+//     COLLECT  + bitonic SORT of the chunk in shared memory, boxes staged (corner-normalised) with their areas.
+//     GREEDY   64 candidates at a time: (a) all threads test the block against the kept list (shared memory,
+//              broadcast reads), (b) all threads build the 64x64 bitmask of the block, (c) one warp resolves the
+//              block with register bit operations and appends the survivors to the kept list.
+//   The loop ends as soon as `cap` boxes are kept -- TF's greedy loop exactly, no pre-NMS cut needed (trap T1).
 __global__ void __launch_bounds__(kNmsThreads, 1)
     nms_select_kernel(const float4* __restrict__ boxes, const uint32_t* __restrict__ keys, int N, int cap, int top_n,
                       float iou_thr, int32_t* __restrict__ kept_idx, int32_t* __restrict__ kept_count,
@@ -105,13 +115,11 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
     // 8-byte items first, then 16-byte boxes, then 4-byte arrays: every sub-array stays naturally aligned for any cap
     NmsShared* S = reinterpret_cast<NmsShared*>(smem_raw);
     unsigned long long* comp = reinterpret_cast<unsigned long long*>(smem_raw + kNmsSharedBytes);  // [kChunk]
-    unsigned long long* mask = comp + kChunk;                                              // [kChunk*kChunkWords]
-    float4* cbox = reinterpret_cast<float4*>(mask + kChunk * kChunkWords);                  // [kChunk]
+    float4* cbox = reinterpret_cast<float4*>(comp + kChunk);                                // [kChunk]
     float4* kbox = cbox + kChunk;                                                          // [cap]
     float* carea = reinterpret_cast<float*>(kbox + cap);                                    // [kChunk]
     float* karea = carea + kChunk;                                                         // [cap]
     unsigned int* hist = reinterpret_cast<unsigned int*>(karea + cap);                      // [kBins]
-    int* alive = reinterpret_cast<int*>(hist + kBins);                                      // [kChunk]
 
     const int seg = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -132,13 +140,17 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
     const int n_rounds = (N + kNmsThreads - 1) / kNmsThreads;
 
     while (true) {
-        // ===================== SELECT: 11-bit MSD radix select on the 64-bit composite ==================
+        // ===================== SELECT ===================================================================
         if (tid == 0) {
             S->pfx = 0;
             S->pmask = 0;
-            S->want = min(kChunk, S->budget);
-            S->need = S->want;
+            const int budget = S->budget;
+            S->want_max = min(kChunk, budget);
+            // exact count only when pre_nms_top_n ends inside this chunk; otherwise any size in [half, full] will do
+            S->want_min = budget <= kChunk ? S->want_max : kChunk / 2;
+            S->need = S->want_max;
             S->select_done = 0;
+            S->expect = 0;
             S->cnt = 0;
         }
         __syncthreads();
@@ -178,13 +190,11 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
                     if (lane >= o) incl += v;
                 }
                 const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
-                int need = S->need;
-                if (pass == 0) {  // total = all unvisited candidates of this segment
+                int need = S->need;            // still wanted from inside the current prefix
+                const int got = S->expect;     // already secured by bins above the current prefix
+                if (pass == 0) {               // total = all unvisited candidates of this segment
                     if ((int)total < need) need = (int)total;
-                    if (lane == 0) {
-                        S->want = need;
-                        S->remaining = (int)total - need;
-                    }
+                    if (lane == 0) S->remaining = (int)total;
                 }
                 const unsigned int excl = incl - sum;
                 if (need > 0 && excl < (unsigned)need && (unsigned)need <= incl) {  // exactly one lane
@@ -196,16 +206,24 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
                             unsigned long long npfx = pfx | (bin << shift);
                             unsigned long long nmask = pmask | ((unsigned long long)(nb - 1) << shift);
                             const int in_bin = need - (int)cum;
-                            if ((int)h == in_bin) {  // whole bin taken: threshold found
+                            if ((int)h == in_bin) {  // whole bin taken: exact threshold
                                 S->thresh = npfx;
+                                S->expect = got + (int)cum + (int)h;
                                 S->select_done = 1;
-                            } else if (pass == 2) {  // bits 22..31 of ~idx are constant ones
-                                npfx |= 0xffc00000ull;
-                                nmask |= 0xffc00000ull;
+                            } else if (got + (int)cum >= S->want_min) {  // bins above this one are enough
+                                S->thresh = npfx + (1ull << shift);      // first composite above the bin
+                                S->expect = got + (int)cum;
+                                S->select_done = 1;
+                            } else {
+                                if (pass == 2) {  // bits 22..31 of ~idx are constant ones
+                                    npfx |= 0xffc00000ull;
+                                    nmask |= 0xffc00000ull;
+                                }
+                                S->expect = got + (int)cum;
+                                S->need = in_bin;
                             }
                             S->pfx = npfx;
                             S->pmask = nmask;
-                            S->need = in_bin;
                             break;
                         }
                         cum += h;
@@ -216,8 +234,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
             __syncthreads();
             if (S->select_done) break;
         }
-        const int want = S->want;
-        if (want == 0) break;  // no candidates left (uniform)
+        const int expect = S->expect;
+        if (expect == 0) break;  // no candidates left (uniform)
         const unsigned long long thresh = S->thresh;
 
         // ===================== COLLECT the chunk (unordered) ===========================================
@@ -242,7 +260,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
             }
         }
         __syncthreads();
-        const int m = min((int)S->cnt, kChunk);  // == want by construction
+        const int m = min((int)S->cnt, kChunk);  // == expect by construction
         int p2 = 32;
         while (p2 < m) p2 <<= 1;
         for (int i = m + tid; i < p2; i += kNmsThreads) comp[i] = 0ull;
@@ -267,72 +285,62 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
         }
 
         // ===================== LOAD boxes (corner-normalised) + areas ===================================
-        if (tid < kChunk) {
-            if (tid < m) {
-                const uint32_t idx = 0xffffffffu - (uint32_t)(comp[tid] & 0xffffffffull);
-                const float4 b = __ldg(sboxes + idx);
-                const float4 nb4 = make_float4(fminf(b.x, b.z), fminf(b.y, b.w), fmaxf(b.x, b.z), fmaxf(b.y, b.w));
-                cbox[tid] = nb4;
-                carea[tid] = fmul(fsub(nb4.z, nb4.x), fsub(nb4.w, nb4.y));
-                alive[tid] = 1;
-            } else {
-                alive[tid] = 0;
-            }
+        if (tid < m) {
+            const uint32_t idx = 0xffffffffu - (uint32_t)(comp[tid] & 0xffffffffull);
+            const float4 b = __ldg(sboxes + idx);
+            const float4 nb4 = make_float4(fminf(b.x, b.z), fminf(b.y, b.w), fmaxf(b.x, b.z), fmaxf(b.y, b.w));
+            cbox[tid] = nb4;
+            carea[tid] = fmul(fsub(nb4.z, nb4.x), fsub(nb4.w, nb4.y));
         }
         __syncthreads();
 
-        // ===================== PHASE A: chunk vs already kept boxes =====================================
-        {
-            const int kept = S->kept;
-            const int t = tid & (kChunk - 1), half = tid / kChunk;  // two threads per candidate
-            if (t < m && kept > 0) {
-                const float4 bt = cbox[t];
-                const float at = carea[t];
-                bool sup = false;
-                for (int j = half; j < kept; j += kNmsThreads / kChunk) {
-                    if (tf_suppresses(bt, at, kbox[j], karea[j], iou_thr)) {
-                        sup = true;
-                        break;
+        // ===================== GREEDY, 64 candidates at a time ==========================================
+        const int nblk = (m + 63) / 64;
+        for (int blk = 0; blk < nblk; ++blk) {
+            const int kept = S->kept;  // uniform: written before the barrier that ended the previous block
+            if (kept >= cap) break;
+            const int base = blk * 64;
+            const int nvalid = min(64, m - base);
+            if (tid < 128) S->diag[tid] = 0u;
+            if (tid < 2) S->dead[tid] = 0u;
+            __syncthreads();
+            {   // (a) block vs kept list: thread = (candidate, one of 16 interleaved slices of the kept list)
+                const int cand = tid & 63, part = tid >> 6;
+                if (cand < nvalid && part < kept) {
+                    const float4 bt = cbox[base + cand];
+                    const float at = carea[base + cand];
+                    bool sup = false;
+                    for (int j = part; j < kept; j += kNmsThreads / 64) {
+                        if (tf_suppresses(bt, at, kbox[j], karea[j], iou_thr)) {
+                            sup = true;
+                            break;
+                        }
                     }
+                    if (sup) atomicOr(&S->dead[cand >> 5], 1u << (cand & 31));
                 }
-                if (sup) alive[t] = 0;
             }
-        }
-        __syncthreads();
-        if (tid < kChunk) {
-            const unsigned bal = __ballot_sync(0xffffffffu, alive[tid] != 0);
-            if (lane == 0) S->alive32[warp] = bal;
-        }
-
-        // ===================== PHASE B: suppression bitmask among the chunk =============================
-        // mask[t][w] bit u: candidate 64w+u (ranked after t) overlaps t by more than the threshold.
-        for (int item = tid; item < m * kChunkWords; item += kNmsThreads) {
-            const int t = item / kChunkWords, w = item % kChunkWords;
-            unsigned long long bits = 0ull;
-            if (alive[t] && (w + 1) * 64 > t + 1 && w * 64 < m) {
-                const float4 bt = cbox[t];
-                const float at = carea[t];
-                const int u0 = max(w * 64, t + 1), u1 = min((w + 1) * 64, m);
-                for (int u = u0; u < u1; ++u)
-                    if (tf_suppresses(bt, at, cbox[u], carea[u], iou_thr)) bits |= 1ull << (u - w * 64);
+            {   // (b) 64x64 upper triangle of the block: thread = (row, group of 4 columns)
+                const int row = tid >> 4, g = tid & 15;
+                if (row < nvalid && 4 * g + 3 > row) {
+                    const float4 bt = cbox[base + row];
+                    const float at = carea[base + row];
+                    unsigned int bits = 0u;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int u = 4 * g + q;
+                        if (u > row && u < nvalid && tf_suppresses(bt, at, cbox[base + u], carea[base + u], iou_thr))
+                            bits |= 1u << q;
+                    }
+                    if (bits) atomicOr(&S->diag[2 * row + (g >> 3)], bits << ((4 * g) & 31));
+                }
             }
-            mask[item] = bits;
-        }
-        __syncthreads();
-
-        // ===================== PHASE C: greedy resolve, 64 candidates at a time (warp 0) ===============
-        if (warp == 0) {
-            int kept = S->kept;
-            unsigned long long removed = 0ull;  // lane w < kChunkWords owns word w
-            const int nblk = (m + 63) / 64;
-            for (int blk = 0; blk < nblk && kept < cap; ++blk) {
-                const unsigned long long alive_w =
-                    (unsigned long long)S->alive32[2 * blk] | ((unsigned long long)S->alive32[2 * blk + 1] << 32);
-                unsigned long long cur = __shfl_sync(0xffffffffu, removed, blk) | ~alive_w;
-                // diagonal words of this block, two rows per lane
-                const int row0 = blk * 64 + lane, row1 = row0 + 32;
-                const unsigned long long d0 = row0 < m ? mask[row0 * kChunkWords + blk] : 0ull;
-                const unsigned long long d1 = row1 < m ? mask[row1 * kChunkWords + blk] : 0ull;
+            __syncthreads();
+            if (warp == 0) {  // (c) resolve: lane l holds the mask rows l and l+32
+                const unsigned long long valid = nvalid == 64 ? ~0ull : ((1ull << nvalid) - 1ull);
+                unsigned long long cur = ((unsigned long long)S->dead[0] | ((unsigned long long)S->dead[1] << 32)) | ~valid;
+                const unsigned long long d0 = (unsigned long long)S->diag[2 * lane] | ((unsigned long long)S->diag[2 * lane + 1] << 32);
+                const unsigned long long d1 =
+                    (unsigned long long)S->diag[2 * (lane + 32)] | ((unsigned long long)S->diag[2 * (lane + 32) + 1] << 32);
                 unsigned long long keepbits = 0ull;
                 int room = cap - kept;
 #pragma unroll
@@ -345,37 +353,29 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
                         --room;
                     }
                 }
-                // append kept boxes (lane handles bits lane and lane+32)
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
+                for (int h = 0; h < 2; ++h) {  // append survivors (lane handles bits lane and lane+32)
                     const int i = lane + 32 * h;
                     if ((keepbits >> i) & 1ull) {
                         const int pos = kept + __popcll(keepbits & ((1ull << i) - 1ull));
-                        const int row = blk * 64 + i;
-                        kbox[pos] = cbox[row];
-                        karea[pos] = carea[row];
-                        sidx[pos] = (int32_t)(0xffffffffu - (uint32_t)(comp[row] & 0xffffffffull));
+                        kbox[pos] = cbox[base + i];
+                        karea[pos] = carea[base + i];
+                        sidx[pos] = (int32_t)(0xffffffffu - (uint32_t)(comp[base + i] & 0xffffffffull));
                     }
                 }
-                kept += __popcll(keepbits);
-                // fold the kept rows into the removed words of later blocks
-                unsigned long long kb = keepbits;
-                while (kb) {
-                    const int i = __ffsll((long long)kb) - 1;
-                    kb &= kb - 1ull;
-                    if (lane < kChunkWords) removed |= mask[(blk * 64 + i) * kChunkWords + lane];
-                }
+                if (lane == 0) S->kept = kept + __popcll(keepbits);
             }
-            if (lane == 0) {
-                S->kept = kept;
-                S->hi = comp[m - 1];
-                S->budget -= m;
-                int stop = 0;
-                if (kept >= cap) stop = 1;
-                else if (S->remaining == 0) stop = 1;                  // every candidate visited
-                else if (S->budget <= 0) stop = 2;                     // pre_nms_top_n cut the list short
-                S->stop = stop;
-            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            S->hi = comp[m - 1];
+            S->budget -= m;
+            S->remaining -= m;
+            int stop = 0;
+            if (S->kept >= cap) stop = 1;
+            else if (S->remaining <= 0) stop = 1;  // every candidate visited
+            else if (S->budget <= 0) stop = 2;     // pre_nms_top_n cut the list short
+            S->stop = stop;
         }
         __syncthreads();
         const int stop = S->stop;
@@ -394,9 +394,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
 }
 
 static size_t nms_smem_bytes(int cap) {
-    return sizeof(unsigned long long) * (kChunk + kChunk * kChunkWords) + sizeof(float4) * (kChunk + (size_t)cap) +
-           sizeof(float) * (kChunk + (size_t)cap) + sizeof(unsigned int) * kBins + sizeof(int) * kChunk +
-           kNmsSharedBytes + 16;
+    return sizeof(unsigned long long) * kChunk + sizeof(float4) * (kChunk + (size_t)cap) +
+           sizeof(float) * (kChunk + (size_t)cap) + sizeof(unsigned int) * kBins + kNmsSharedBytes + 16;
 }
 
 // ------------------------------------------------------------------------------------------------

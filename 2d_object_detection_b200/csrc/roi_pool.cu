@@ -241,7 +241,7 @@ __device__ __forceinline__ void walk_bin_row(const float4* __restrict__ f, const
 
 // grid (R, B); T threads; each thread owns VPT float4 channel vectors per pass over the channels.
 template <int VPT, int T>
-__global__ void __launch_bounds__(T, 512 / T)
+__global__ void __launch_bounds__(T, VPT == 2 ? 3 : 512 / T)
     roi_pool_fwd_k2_kernel(const float4* __restrict__ feat, int Hf, int Wf, int CV, const float4* __restrict__ rois, int R,
                            int P, float4* __restrict__ out) {
     __shared__ AxisTab ty, tx;
