@@ -139,6 +139,27 @@ struct AxisX {             // per crop column: feature cell (left column index, 
     float lerp[kMaxCrop];
 };
 
+// Packed fp32x2 lerp a + (b - a) * w for a float4 (Blackwell FADD2 / FMUL2: two fp32 lanes per issue slot).
+// Every element still sees sub.rn, mul.rn, add.rn separately rounded, i.e. the same bits as lerpv().  The final
+// add stays scalar on purpose: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (single rounding) even
+// under -fmad=false, which would break bit parity with the reference's unfused CPU arithmetic.
+__device__ __forceinline__ float4 lerp_packed(const float4& a, const float4& b, float w) {
+    unsigned long long a0, a1, b0, b1, d0, d1, ww;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(a0) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(a1) : "f"(a.z), "f"(a.w));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(b0) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(b1) : "f"(b.z), "f"(b.w));
+    asm("mov.b64 %0, {%1,%1};" : "=l"(ww) : "f"(w));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d0) : "l"(b0), "l"(a0));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d1) : "l"(b1), "l"(a1));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d0) : "l"(d0), "l"(ww));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d1) : "l"(d1), "l"(ww));
+    float p0, p1, p2, p3;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(p0), "=f"(p1) : "l"(d0));
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(p2), "=f"(p3) : "l"(d1));
+    return make_float4(fadd(a.x, p0), fadd(a.y, p1), fadd(a.z, p2), fadd(a.w, p3));
+}
+
 __device__ __forceinline__ float4 vmax4(const float4& a, const float4& b) {
     return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
 }
@@ -185,29 +206,29 @@ __device__ __forceinline__ void walk_bin_row(const float4* __restrict__ f, const
             for (int v = 0; v < VPT; ++v) best[v] = zero;
         }
     };
+    auto sample_v = [&](const float4 (&L)[NR][VPT], const float4 (&Rt)[NR][VPT], float xl, int v) -> float4 {
+        float4 X[NR];
+#pragma unroll
+        for (int k = 0; k < NR; ++k) X[k] = lerp_packed(L[k][v], Rt[k][v], xl);
+        float4 s0 = lerp_packed(X[0], X[1], yl0);
+        float4 s1 = NR == 2 ? lerp_packed(X[0], X[1], yl1)
+                            : NR == 3 ? lerp_packed(X[1], X[2], yl1) : lerp_packed(X[NR - 2], X[NR - 1], yl1);
+        if (kCheckY) {
+            if (!yv0) s0 = zero;  // extrapolation_value = 0 for a crop row outside the map
+            if (!yv1) s1 = zero;
+        }
+        return vmax4(s0, s1);
+    };
+    // even crop column: first half of a bin, result goes straight into `best`; odd: finish the bin and store it
     auto emit = [&](int sx, const float4 (&L)[NR][VPT], const float4 (&Rt)[NR][VPT]) {
         const float xl = ax.lerp[sx];
-        float4 m[VPT];
-#pragma unroll
-        for (int v = 0; v < VPT; ++v) {
-            float4 X[NR];
-#pragma unroll
-            for (int k = 0; k < NR; ++k) X[k] = lerpv(L[k][v], Rt[k][v], xl);
-            float4 s0 = lerpv(X[0], X[1], yl0);
-            float4 s1 = NR == 2 ? lerpv(X[0], X[1], yl1) : NR == 3 ? lerpv(X[1], X[2], yl1) : lerpv(X[NR - 2], X[NR - 1], yl1);
-            if (kCheckY) {
-                if (!yv0) s0 = zero;  // extrapolation_value = 0 for a crop row outside the map
-                if (!yv1) s1 = zero;
-            }
-            m[v] = vmax4(s0, s1);
-        }
         if (sx & 1) {
 #pragma unroll
-            for (int v = 0; v < VPT; ++v) st_cs_f4(optr + v * T, vmax4(best[v], m[v]));
+            for (int v = 0; v < VPT; ++v) st_cs_f4(optr + v * T, vmax4(best[v], sample_v(L, Rt, xl, v)));
             optr += CV;
         } else {
 #pragma unroll
-            for (int v = 0; v < VPT; ++v) best[v] = m[v];
+            for (int v = 0; v < VPT; ++v) best[v] = sample_v(L, Rt, xl, v);
         }
     };
     int sx = 0;
@@ -241,7 +262,7 @@ __device__ __forceinline__ void walk_bin_row(const float4* __restrict__ f, const
 
 // grid (R, B); T threads; each thread owns VPT float4 channel vectors per pass over the channels.
 template <int VPT, int T>
-__global__ void __launch_bounds__(T, VPT == 2 ? 3 : 512 / T)
+__global__ void __launch_bounds__(T, 512 / T)
     roi_pool_fwd_k2_kernel(const float4* __restrict__ feat, int Hf, int Wf, int CV, const float4* __restrict__ rois, int R,
                            int P, float4* __restrict__ out) {
     __shared__ AxisTab ty, tx;
@@ -281,8 +302,12 @@ __global__ void __launch_bounds__(T, VPT == 2 ? 3 : 512 / T)
                 const int roff[4] = {t0, b0, b1, 0};
                 walk_bin_row<3, false, VPT, T>(f, roff, yl0, yl1, true, true, ax, S, Wf - 1, CV, orow);
             } else {
+                // rare / large-RoI shape: one channel vector at a time keeps the register budget of the kernel at
+                // what the common 2- and 3-row shapes need (occupancy is set by the worst path)
                 const int roff[4] = {t0, b0, t1, b1};
-                walk_bin_row<4, true, VPT, T>(f, roff, yl0, yl1, yv0, yv1, ax, S, Wf - 1, CV, orow);
+#pragma unroll 1
+                for (int v = 0; v < VPT; ++v)
+                    walk_bin_row<4, true, 1, T>(f + v * T, roff, yl0, yl1, yv0, yv1, ax, S, Wf - 1, CV, orow + v * T);
             }
         }
     }

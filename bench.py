@@ -60,6 +60,13 @@ def config_dict(w, args, extra=None):
 
 
 # ------------------------------------------------------------------------------------------ CPU baseline
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:  # pragma: no cover
+        return os.cpu_count() or 1
+
+
 def cpu_path_step(oracle, w, anchors, scores, deltas, feat):
     """The reference's CPU path for one batch: postprocess_output -> ROIPooling (oracle port, OpenMP)."""
     out = oracle.postprocess_output(w.image_shape, anchors, scores, deltas, **w.nms_kwargs(), pre_nms_top_n=w.pre_nms_top_n)
@@ -70,6 +77,7 @@ def cpu_path_step(oracle, w, anchors, scores, deltas, feat):
 def time_cpu_baseline(w, syn, images, budget_s=20.0, min_reps=2, max_reps=50):
     import oracle
     oracle.build()
+    oracle.set_num_threads(host_threads())
     anchors = oracle.clip_to_window(oracle.generate_anchors(w.grid, w.scales, w.aspect_ratios, w.base_anchor_shape),
                                     [0, 0, w.image_shape[1], w.image_shape[0]])
     scores, deltas, feat = make_inputs(syn, w, images, 777)
@@ -92,6 +100,7 @@ def run_reference_arm(args, w, syn):
         return 0
     import oracle
     oracle.build()
+    oracle.set_num_threads(host_threads())  # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host thread
     anchors = oracle.clip_to_window(oracle.generate_anchors(w.grid, w.scales, w.aspect_ratios, w.base_anchor_shape),
                                     [0, 0, w.image_shape[1], w.image_shape[0]])
     # bounded sample: a whole per-GPU batch unless that would push the run past a few minutes
