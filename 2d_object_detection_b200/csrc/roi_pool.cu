@@ -397,6 +397,274 @@ __global__ void __launch_bounds__(kRoiThreads)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fast backward path for kernel_size == 2, float4 channels, pooled_size <= 8.  Per bin-row, two walks:
+//   pass 1  the forward walk again, but instead of storing the maximum it records WHICH of the four crop
+//           samples won, per channel (first maximum in row-major window order, strict >: trap T8), as 2-bit
+//           codes in one 64-bit register per channel vector (7 bins x 4 channels x 2 bits);
+//   pass 2  the same cells once more with the incoming gradient: every sample adds its four bilinear shares
+//           (weights (1-xl)(1-yl) etc., one packed FMA each) into REGISTER accumulators for the
+//           left / right feature column of the current cell; a column is flushed with one 16-byte vector
+//           reduction per row (red.global.add.v4.f32) only when the walk leaves it.  That aggregates all
+//           samples of a bin-row that share a feature pixel into a single atomic, instead of up to 16 per bin.
+// ------------------------------------------------------------------------------------------------
+template <int NR, bool kCheckY, int VPT, int T>
+__device__ __forceinline__ void argmax_bin_row(const float4* __restrict__ f, const int (&roff)[4], float yl0, float yl1,
+                                               bool yv0, bool yv1, const AxisX& ax, int S, int last_col, int CV,
+                                               unsigned long long (&codes)[VPT]) {
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* fr[NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) fr[k] = f + roff[k];
+    float4 A[NR][VPT], B[NR][VPT];
+    float4 e0[VPT], e1[VPT];  // the two even-column samples of the current bin (window positions (0,0) and (1,0))
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) codes[v] = 0ull;
+    auto load_col = [&](float4 (&dst)[NR][VPT], int col) {
+        const int off = min(col, last_col) * CV;
+#pragma unroll
+        for (int k = 0; k < NR; ++k) {
+            const float4* p = fr[k] + off;
+#pragma unroll
+            for (int v = 0; v < VPT; ++v) dst[k][v] = __ldg(p + v * T);
+        }
+    };
+    auto pick = [&](float a00, float a01, float a10, float a11) -> unsigned {
+        float best = a00;
+        unsigned arg = 0u;
+        if (a01 > best) { best = a01; arg = 1u; }
+        if (a10 > best) { best = a10; arg = 2u; }
+        if (a11 > best) { arg = 3u; }
+        return arg;
+    };
+    auto finish = [&](int sx, int v, const float4& o0, const float4& o1) {
+        const unsigned cb = pick(e0[v].x, o0.x, e1[v].x, o1.x) | (pick(e0[v].y, o0.y, e1[v].y, o1.y) << 2) |
+                            (pick(e0[v].z, o0.z, e1[v].z, o1.z) << 4) | (pick(e0[v].w, o0.w, e1[v].w, o1.w) << 6);
+        codes[v] |= (unsigned long long)cb << ((sx >> 1) * 8);
+    };
+    auto emit_zero = [&](int sx) {
+#pragma unroll
+        for (int v = 0; v < VPT; ++v) {
+            if (sx & 1) finish(sx, v, zero, zero);
+            else e0[v] = e1[v] = zero;
+        }
+    };
+    auto emit = [&](int sx, const float4 (&L)[NR][VPT], const float4 (&Rt)[NR][VPT]) {
+        const float xl = ax.lerp[sx];
+#pragma unroll
+        for (int v = 0; v < VPT; ++v) {
+            float4 X[NR];
+#pragma unroll
+            for (int k = 0; k < NR; ++k) X[k] = lerp_packed(L[k][v], Rt[k][v], xl);
+            float4 s0 = lerp_packed(X[0], X[1], yl0);
+            float4 s1 = NR == 2 ? lerp_packed(X[0], X[1], yl1)
+                                : NR == 3 ? lerp_packed(X[1], X[2], yl1) : lerp_packed(X[NR - 2], X[NR - 1], yl1);
+            if (kCheckY) {
+                if (!yv0) s0 = zero;
+                if (!yv1) s1 = zero;
+            }
+            if (sx & 1) finish(sx, v, s0, s1);
+            else { e0[v] = s0; e1[v] = s1; }
+        }
+    };
+    int sx = 0;
+    while (sx < S) {
+        int c = ax.cell[sx];
+        if (c < 0) {
+            emit_zero(sx);
+            ++sx;
+            continue;
+        }
+        load_col(A, c);
+        load_col(B, c + 1);
+        for (;;) {
+            do {
+                emit(sx, A, B);
+                ++sx;
+            } while (sx < S && ax.cell[sx] == c);
+            if (sx >= S || ax.cell[sx] != c + 1) break;
+            ++c;
+            load_col(A, c + 1);
+            do {
+                emit(sx, B, A);
+                ++sx;
+            } while (sx < S && ax.cell[sx] == c);
+            if (sx >= S || ax.cell[sx] != c + 1) break;
+            ++c;
+            load_col(B, c + 1);
+        }
+    }
+}
+
+// acc + w * x with packed fused multiply-adds (FFMA2).  The gradient has no reference summation order (TF's GPU
+// kernel uses atomics, its CPU kernel a sequential loop) and its bar is 1e-5 relative, so the backward may fuse:
+// one rounding per contribution instead of TF's three ((1-yl)*g, (1-xl)*dtop, +=) -- closer to the exact sum.
+__device__ __forceinline__ void axpy_packed(float4& acc, float w, const float4& x) {
+    unsigned long long a0, a1, x0, x1, ww;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(a0) : "f"(acc.x), "f"(acc.y));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(a1) : "f"(acc.z), "f"(acc.w));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(x0) : "f"(x.x), "f"(x.y));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(x1) : "f"(x.z), "f"(x.w));
+    asm("mov.b64 %0, {%1,%1};" : "=l"(ww) : "f"(w));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a0) : "l"(x0), "l"(ww));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a1) : "l"(x1), "l"(ww));
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(a0));
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(acc.z), "=f"(acc.w) : "l"(a1));
+}
+
+template <int NR, bool kCheckY, int VPT, int T>
+__device__ __forceinline__ void scatter_bin_row(float4* __restrict__ g_base, const int (&roff)[4], float yl0, float yl1,
+                                                bool yv0, bool yv1, const AxisX& ax, int S, int last_col, int CV,
+                                                const float4* __restrict__ gy_row,
+                                                const unsigned long long (&codes)[VPT]) {
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4* gr[NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) gr[k] = g_base + roff[k];
+    float4 A[NR][VPT], B[NR][VPT];  // gradient accumulated for feature columns c (left) and c+1 (right)
+    float4 g[VPT];
+    int g_bin = -1;
+    auto clear = [&](float4 (&acc)[NR][VPT]) {
+#pragma unroll
+        for (int k = 0; k < NR; ++k)
+#pragma unroll
+            for (int v = 0; v < VPT; ++v) acc[k][v] = zero;
+    };
+    auto flush = [&](const float4 (&acc)[NR][VPT], int col) {
+        const int off = min(col, last_col) * CV;
+#pragma unroll
+        for (int k = 0; k < NR; ++k)
+#pragma unroll
+            for (int v = 0; v < VPT; ++v) red_add_f4(gr[k] + off + v * T, acc[k][v]);
+    };
+    // rows under crop row 1: NR==2 -> (0,1), NR==3 -> (1,2), NR==4 -> (2,3); crop row 0 always (0,1)
+    constexpr int kT1 = NR == 2 ? 0 : NR == 3 ? 1 : 2;
+    constexpr int kB1 = kT1 + 1;
+    auto accumulate = [&](int sx, float4 (&L)[NR][VPT], float4 (&Rt)[NR][VPT]) {
+        const int px = sx >> 1;
+        const unsigned dx = (unsigned)(sx & 1);
+        if (g_bin != px) {
+#pragma unroll
+            for (int v = 0; v < VPT; ++v) g[v] = ld_nc_f4(gy_row + (size_t)px * CV + v * T);
+            g_bin = px;
+        }
+        const float xl = ax.lerp[sx];
+        const float wl = fsub(1.0f, xl);
+#pragma unroll
+        for (int v = 0; v < VPT; ++v) {
+            const unsigned cb = (unsigned)(codes[v] >> (px * 8)) & 0xffu;
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+                if (kCheckY && !(dy == 0 ? yv0 : yv1)) continue;  // crop row outside the map contributes nothing
+                const unsigned id = (unsigned)dy * 2u + dx;
+                const float4 gs = make_float4(((cb >> 0) & 3u) == id ? g[v].x : 0.f, ((cb >> 2) & 3u) == id ? g[v].y : 0.f,
+                                              ((cb >> 4) & 3u) == id ? g[v].z : 0.f, ((cb >> 6) & 3u) == id ? g[v].w : 0.f);
+                const float yl = dy == 0 ? yl0 : yl1;
+                const float wt = fsub(1.0f, yl);
+                const int kt = dy == 0 ? 0 : kT1, kb = dy == 0 ? 1 : kB1;
+                axpy_packed(L[kt][v], fmul(wl, wt), gs);   // (1-xl)(1-yl) g -> top-left
+                axpy_packed(Rt[kt][v], fmul(xl, wt), gs);  //    xl (1-yl) g -> top-right
+                axpy_packed(L[kb][v], fmul(wl, yl), gs);   // (1-xl)   yl  g -> bottom-left
+                axpy_packed(Rt[kb][v], fmul(xl, yl), gs);  //    xl    yl  g -> bottom-right
+            }
+        }
+    };
+    int sx = 0;
+    while (sx < S) {
+        int c = ax.cell[sx];
+        if (c < 0) {  // crop column outside the map: no gradient
+            ++sx;
+            continue;
+        }
+        clear(A);
+        clear(B);
+        for (;;) {
+            do {  // left = A (column c), right = B (column c+1)
+                accumulate(sx, A, B);
+                ++sx;
+            } while (sx < S && ax.cell[sx] == c);
+            if (sx >= S || ax.cell[sx] != c + 1) {
+                flush(A, c);
+                flush(B, c + 1);
+                break;
+            }
+            flush(A, c);
+            clear(A);
+            ++c;
+            do {  // left = B (column c), right = A (column c+1)
+                accumulate(sx, B, A);
+                ++sx;
+            } while (sx < S && ax.cell[sx] == c);
+            if (sx >= S || ax.cell[sx] != c + 1) {
+                flush(B, c);
+                flush(A, c + 1);
+                break;
+            }
+            flush(B, c);
+            clear(B);
+            ++c;
+        }
+    }
+}
+
+template <int VPT, int T>
+__global__ void __launch_bounds__(T, VPT == 2 ? 3 : 512 / T)
+    roi_pool_bwd_k2_kernel(const float4* __restrict__ feat, int Hf, int Wf, int CV, const float4* __restrict__ rois, int R,
+                           int P, const float4* __restrict__ dy_in, float4* __restrict__ dfeat) {
+    __shared__ AxisTab ty, tx;
+    __shared__ AxisY ay;
+    __shared__ AxisX ax;
+    const int r = blockIdx.x, b = blockIdx.y;
+    const int S = 2 * P;
+    const float4 roi = rois[(size_t)b * R + r];
+    if (threadIdx.x < S) {
+        const int i = threadIdx.x;
+        axis_sample(roi.y, roi.w, Hf, S, i, ty);
+        ay.lo[i] = ty.lo[i] * Wf * CV;
+        ay.hi[i] = ty.hi[i] * Wf * CV;
+        ay.lerp[i] = ty.lerp[i];
+        ay.valid[i] = ty.valid[i];
+    } else if (threadIdx.x >= 32 && threadIdx.x < 32 + S) {
+        const int i = threadIdx.x - 32;
+        axis_sample(roi.x, roi.z, Wf, S, i, tx);
+        ax.cell[i] = tx.valid[i] ? tx.lo[i] : -1;
+        ax.lerp[i] = tx.lerp[i];
+    }
+    __syncthreads();
+    const float4* fb = feat + (size_t)b * Hf * Wf * CV;
+    float4* gb = dfeat + (size_t)b * Hf * Wf * CV;
+    const float4* gy = dy_in + ((size_t)b * R + r) * P * P * CV;
+    for (int cv = threadIdx.x; cv < CV; cv += T * VPT) {
+        for (int py = 0; py < P; ++py) {
+            const int sy0 = 2 * py, sy1 = sy0 + 1;
+            const int t0 = ay.lo[sy0], b0 = ay.hi[sy0], t1 = ay.lo[sy1], b1 = ay.hi[sy1];
+            const float yl0 = ay.lerp[sy0], yl1 = ay.lerp[sy1];
+            const bool yv0 = ay.valid[sy0] != 0, yv1 = ay.valid[sy1] != 0;
+            const float4* gy_row = gy + (size_t)py * P * CV + cv;
+            if (yv0 && yv1 && t1 == t0 && b1 == b0) {
+                const int roff[4] = {t0, b0, 0, 0};
+                unsigned long long codes[VPT];
+                argmax_bin_row<2, false, VPT, T>(fb + cv, roff, yl0, yl1, true, true, ax, S, Wf - 1, CV, codes);
+                scatter_bin_row<2, false, VPT, T>(gb + cv, roff, yl0, yl1, true, true, ax, S, Wf - 1, CV, gy_row, codes);
+            } else if (yv0 && yv1 && t1 == b0) {
+                const int roff[4] = {t0, b0, b1, 0};
+                unsigned long long codes[VPT];
+                argmax_bin_row<3, false, VPT, T>(fb + cv, roff, yl0, yl1, true, true, ax, S, Wf - 1, CV, codes);
+                scatter_bin_row<3, false, VPT, T>(gb + cv, roff, yl0, yl1, true, true, ax, S, Wf - 1, CV, gy_row, codes);
+            } else {
+                const int roff[4] = {t0, b0, t1, b1};
+#pragma unroll 1
+                for (int v = 0; v < VPT; ++v) {
+                    unsigned long long codes[1];
+                    argmax_bin_row<4, true, 1, T>(fb + cv + v * T, roff, yl0, yl1, yv0, yv1, ax, S, Wf - 1, CV, codes);
+                    scatter_bin_row<4, true, 1, T>(gb + cv + v * T, roff, yl0, yl1, yv0, yv1, ax, S, Wf - 1, CV,
+                                                   gy_row + v * T, codes);
+                }
+            }
+        }
+    }
+}
+
 }  // namespace frcnn
 
 using namespace frcnn;
@@ -446,7 +714,18 @@ int frcnn_roi_pool_backward(const float* feat, int B, int Hf, int Wf, int C, con
     FRCNN_CUDA(cudaMemsetAsync(dfeat, 0, sizeof(float) * (size_t)B * Hf * Wf * C, as_stream(stream)));
     if (R == 0) return 0;
     const dim3 grid(R, B);
-    if (C % 4 == 0)
+    if (C % 4 == 0 && k == 2 && P <= 8 && (int64_t)Hf * Wf * (C / 4) < (1ll << 31)) {
+        const int cv = C / 4;
+        if (cv % 256 == 0)
+            roi_pool_bwd_k2_kernel<2, 128><<<grid, 128, 0, as_stream(stream)>>>(
+                (const float4*)feat, Hf, Wf, cv, (const float4*)rois, R, P, (const float4*)dy, (float4*)dfeat);
+        else if (cv > 64)
+            roi_pool_bwd_k2_kernel<1, 128><<<grid, 128, 0, as_stream(stream)>>>(
+                (const float4*)feat, Hf, Wf, cv, (const float4*)rois, R, P, (const float4*)dy, (float4*)dfeat);
+        else
+            roi_pool_bwd_k2_kernel<1, 64><<<grid, 64, 0, as_stream(stream)>>>(
+                (const float4*)feat, Hf, Wf, cv, (const float4*)rois, R, P, (const float4*)dy, (float4*)dfeat);
+    } else if (C % 4 == 0)
         roi_pool_bwd_kernel<float4><<<grid, kRoiThreads, 0, as_stream(stream)>>>(
             (const float4*)feat, Hf, Wf, C / 4, (const float4*)rois, R, P, k, (const float4*)dy, (float4*)dfeat);
     else

@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""Per-stage device timings (CUDA events, device-resident inputs) for the configurations of BASELINE.json that are
+not the headline bench line: dense-anchor stress forward, and the training path (target matching + RoI-pool
+backward).  Prints one JSON object per stage; algorithmic bytes follow BASELINE.md section 3."""
+import importlib
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+det = importlib.import_module("2d_object_detection_b200")
+syn = det.synthetic
+PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+
+
+def timeit(fn, iters=20, warmup=3, flush=None):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()  # write a buffer larger than L2 between timed iterations
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts))
+
+
+def report(name, workload, ms, alg_bytes, extra=None):
+    gbs = alg_bytes / (ms * 1e-3) / 1e9
+    d = {"stage": name, "workload": workload, "ms": ms, "algorithmic_bytes": alg_bytes, "GB/s": gbs, "frac_of_measured_hbm": gbs / PEAK}
+    d.update(extra or {})
+    print(json.dumps(d), flush=True)
+
+
+def main():
+    dev = torch.device("cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    rng = np.random.default_rng(5)
+    for wname in ("kitti_b8", "dense_b16"):
+        w = syn.WORKLOADS[wname]
+        B, N, R, C = w.batch, w.num_anchors, w.max_total_size, w.channels
+        Hf, Wf = w.grid
+        anchors = det.clip_to_window(det.generate_anchors(w.grid, w.scales, w.aspect_ratios, w.base_anchor_shape), [0, 0, w.image_shape[1], w.image_shape[0]])
+        scores, deltas = syn.rpn_head_outputs(rng, B, N)
+        scores, deltas = torch.as_tensor(scores).to(dev), torch.as_tensor(deltas).to(dev)
+        feat = torch.as_tensor(syn.feature_maps(rng, B, w.grid, C)).to(dev)
+        kw = w.nms_kwargs()
+        out = det.postprocess_output(w.image_shape, anchors, scores, deltas, **kw, pre_nms_top_n=w.pre_nms_top_n, return_extra=True)
+        K = w.pre_nms_top_n or N
+        ms = timeit(lambda: det.postprocess_output(w.image_shape, anchors, scores, deltas, **kw, pre_nms_top_n=w.pre_nms_top_n), flush=flush)
+        report("postprocess_output (decode+NMS+finalize)", wname, ms, B * (44 * N + 4 * N + 40 * K + 16 * K + 16 * K * ((K + 63) // 64) + 24 * R),
+               {"exhausted_images": int(out["exhausted"].sum()), "num_valid_min": int(out["num_valid_detections"].min())})
+        ms = timeit(lambda: det.postprocess_output(w.image_shape, anchors, scores, deltas, **kw, pre_nms_top_n=None), flush=flush)
+        report("postprocess_output, no pre-NMS cap (reference behaviour)", wname, ms, B * (44 * N + 4 * N + 40 * N + 24 * R))
+        rois = out["pred_boxes"]
+        ms = timeit(lambda: det.roi_pool_forward(feat, rois, 7, 2), flush=flush)
+        report("roi_pool_forward", wname, ms, 4 * C * (Hf * Wf + 49 * R) * B)
+        dy = torch.randn((B, R, 7, 7, C), device=dev)
+        ms = timeit(lambda: det.roi_pool_backward(feat, rois, dy, 7, 2), iters=10, flush=flush)
+        report("roi_pool_backward", wname, ms, 4 * C * (49 * R + 3 * Hf * Wf) * B)
+        del dy
+        # training path: target matching on the valid anchors (RPN) and on the proposals (RCNN)
+        a_all = det.generate_anchors(w.grid, w.scales, w.aspect_ratios, w.base_anchor_shape)
+        valid = a_all[det.valid_anchor_indices(a_all, w.image_shape)].contiguous()
+        gl, gb = syn.ground_truth(rng, B)
+        obj = det.rpn_objectness_labels(torch.as_tensor(gl).to(dev))
+        glt, gbt = torch.as_tensor(gl).to(dev), torch.as_tensor(gb).to(dev)
+        ms = timeit(lambda: det.generate_targets_batched(obj, gbt, valid, w.image_shape, [0.7, 1.0], [0.0, 0.3]), flush=flush)
+        report("generate_targets RPN (N_valid x 100)", wname, ms, 40 * valid.shape[0] * B, {"N_valid": int(valid.shape[0])})
+        rois_abs = det.to_absolute(rois, w.image_shape)
+        ms = timeit(lambda: det.generate_targets_batched(glt, gbt, rois_abs, w.image_shape, [0.5, 1.0], [0.0, 0.5]), flush=flush)
+        report("generate_targets RCNN (R x G', 7 classes)", wname, ms, (16 + 4 * 8 + 16 * 7) * R * B)
+
+
+if __name__ == "__main__":
+    main()

@@ -236,10 +236,14 @@ def test_roi_pool_other_window_sizes_and_out_of_range(det, orc, syn, rng):
         np.testing.assert_array_equal(host(det.roi_pool_forward(dev(f), dev(rois), P, k)), orc.roi_pool_forward(f, rois, P, k))
 
 
-@pytest.mark.parametrize("grid,C,R,relu", [((24, 78), 256, 30, True), ((6, 9), 64, 9, False), ((7, 5), 3, 5, True)])
+@pytest.mark.parametrize("grid,C,R,relu", [((24, 78), 256, 30, True), ((6, 9), 64, 9, False), ((7, 5), 3, 5, True),
+                                           ((12, 20), 1024, 12, True), ((9, 11), 512, 8, False)])
 def test_roi_pool_backward(det, orc, syn, rng, grid, C, R, relu):
     f = syn.feature_maps(rng, 2, grid, C, relu=relu)
     rois = syn.random_rois(rng, 2, R, num_valid=[R - 3, R])
+    rois[1, 0] = [0.0, 0.0, 1.0, 1.0]          # whole map: 4-row bin-rows, right neighbour beyond the last column
+    rois[1, 1] = [0.9, 0.8, 0.1, 0.2]          # flipped box: cells walk right to left
+    rois[1, 2] = [-0.2, 0.3, 0.4, 1.3]         # partly outside: zero-filled samples can win the max
     dy = rng.standard_normal((2, R, 7, 7, C)).astype(F)
     ref = orc.roi_pool_backward(f, rois, dy, 7, 2)
     got = host(det.roi_pool_backward(dev(f), dev(rois), dev(dy), 7, 2))
