@@ -194,7 +194,8 @@ class ClockSampler(threading.Thread):
 
     def stop(self):
         self._stop_evt.set()
-        self.join(timeout=2)
+        if self.is_alive():
+            self.join(timeout=2)
         out = {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
                "reasons": sorted(self.reasons), "samples": len(self.samples)}
         if self.err:
@@ -261,16 +262,18 @@ def run_b200_arm(args, w, syn):
         step(i, eng)
     eng.drain()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    t_begin = torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank)  # NVML initialised here, outside the timed region; no background thread, so
+    t_begin = torch.cuda.Event(enable_timing=True)  # nothing competes with the launch loop for the GIL
     t_end = torch.cuda.Event(enable_timing=True)
     t_begin.record()
     eng.attach()
     pool_events = [step(i, eng) for i in range(args.steps)]
-    sampler.sample_once()  # the host runs ahead of the device: the GPU is still inside the timed region here
     eng.drain()
     t_end.record()
+    # the host runs ahead of the device: poll the clocks while the GPU is still inside the timed region
+    sampler.sample_once()
+    while not t_end.query():
+        sampler.sample_once()
     barrier()
     clocks = sampler.stop()
     ms_total = sh.max_over_ranks(t_begin.elapsed_time(t_end), device)
