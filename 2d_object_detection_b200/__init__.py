@@ -23,7 +23,8 @@ from . import _lib
 _lib.load()  # fail loudly at import if the CUDA library has not been built
 
 from . import engine, sharding, synthetic  # noqa: E402
-from .models.detectors.fast_rcnn_detector import ROIPooling, roi_pool_backward, roi_pool_forward  # noqa: E402
+from .models.detectors.fast_rcnn_detector import (ROIPooling, roi_pool_backward, roi_pool_backward_argmax,  # noqa: E402
+                                                  roi_pool_forward, roi_pool_forward_argmax)
 from .models.detectors.rpn_detector import (RPNAnchors, generate_anchors,  # noqa: E402
                                             remove_invalid_anchors_and_predictions, valid_anchor_indices)
 from .pipeline import ProposalRoIPipeline  # noqa: E402

@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(kRoiThreads)
 template <int NR, bool kCheckY, int VPT, int T>
 __device__ __forceinline__ void argmax_bin_row(const float4* __restrict__ f, const int (&roff)[4], float yl0, float yl1,
                                                bool yv0, bool yv1, const AxisX& ax, int S, int last_col, int CV,
-                                               unsigned long long (&codes)[VPT]) {
+                                               unsigned long long (&codes)[VPT], float4* __restrict__ orow = nullptr) {
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4* fr[NR];
 #pragma unroll
@@ -441,6 +441,8 @@ __device__ __forceinline__ void argmax_bin_row(const float4* __restrict__ f, con
         const unsigned cb = pick(e0[v].x, o0.x, e1[v].x, o1.x) | (pick(e0[v].y, o0.y, e1[v].y, o1.y) << 2) |
                             (pick(e0[v].z, o0.z, e1[v].z, o1.z) << 4) | (pick(e0[v].w, o0.w, e1[v].w, o1.w) << 6);
         codes[v] |= (unsigned long long)cb << ((sx >> 1) * 8);
+        if (orow)  // forward-with-argmax: also the pooled value (same max as roi_pool_fwd_k2_kernel)
+            st_cs_f4(orow + (size_t)(sx >> 1) * CV + v * T, vmax4(vmax4(e0[v], o0), vmax4(e1[v], o1)));
     };
     auto emit_zero = [&](int sx) {
 #pragma unroll
@@ -665,6 +667,112 @@ __global__ void __launch_bounds__(T, VPT == 2 ? 3 : 512 / T)
     }
 }
 
+// Training-mode forward: pooled output plus the arg-max codes ([B,R,P,P,CV] bytes: four 2-bit codes per float4),
+// so that the backward pass needs neither the feature maps nor a second interpolation pass.
+// MODE 0: forward + codes.  MODE 1: backward from saved codes (pass 2 of roi_pool_bwd_k2_kernel only).
+template <int VPT, int T, int MODE>
+__global__ void __launch_bounds__(T, VPT == 2 ? 3 : 512 / T)
+    roi_pool_codes_kernel(const float4* __restrict__ feat, int Hf, int Wf, int CV, const float4* __restrict__ rois, int R,
+                          int P, float4* __restrict__ out, unsigned char* __restrict__ codes_io,
+                          const float4* __restrict__ dy_in, float4* __restrict__ dfeat) {
+    __shared__ AxisTab ty, tx;
+    __shared__ AxisY ay;
+    __shared__ AxisX ax;
+    const int r = blockIdx.x, b = blockIdx.y;
+    const int S = 2 * P;
+    const float4 roi = rois[(size_t)b * R + r];
+    if (threadIdx.x < S) {
+        const int i = threadIdx.x;
+        axis_sample(roi.y, roi.w, Hf, S, i, ty);
+        ay.lo[i] = ty.lo[i] * Wf * CV;
+        ay.hi[i] = ty.hi[i] * Wf * CV;
+        ay.lerp[i] = ty.lerp[i];
+        ay.valid[i] = ty.valid[i];
+    } else if (threadIdx.x >= 32 && threadIdx.x < 32 + S) {
+        const int i = threadIdx.x - 32;
+        axis_sample(roi.x, roi.z, Wf, S, i, tx);
+        ax.cell[i] = tx.valid[i] ? tx.lo[i] : -1;
+        ax.lerp[i] = tx.lerp[i];
+    }
+    __syncthreads();
+    const size_t bin0 = ((size_t)b * R + r) * P * P;
+    for (int cv = threadIdx.x; cv < CV; cv += T * VPT) {
+        for (int py = 0; py < P; ++py) {
+            const int sy0 = 2 * py, sy1 = sy0 + 1;
+            const int t0 = ay.lo[sy0], b0 = ay.hi[sy0], t1 = ay.lo[sy1], b1 = ay.hi[sy1];
+            const float yl0 = ay.lerp[sy0], yl1 = ay.lerp[sy1];
+            const bool yv0 = ay.valid[sy0] != 0, yv1 = ay.valid[sy1] != 0;
+            unsigned char* crow = codes_io + (bin0 + (size_t)py * P) * CV + cv;  // + px*CV + v*T
+            const int shape = (yv0 && yv1 && t1 == t0 && b1 == b0) ? 2 : (yv0 && yv1 && t1 == b0) ? 3 : 4;
+            if (MODE == 0) {
+                const float4* f = feat + (size_t)b * Hf * Wf * CV + cv;
+                float4* orow = out + (bin0 + (size_t)py * P) * CV + cv;
+                unsigned long long codes[VPT];
+                if (shape == 2) {
+                    const int roff[4] = {t0, b0, 0, 0};
+                    argmax_bin_row<2, false, VPT, T>(f, roff, yl0, yl1, true, true, ax, S, Wf - 1, CV, codes, orow);
+                } else if (shape == 3) {
+                    const int roff[4] = {t0, b0, b1, 0};
+                    argmax_bin_row<3, false, VPT, T>(f, roff, yl0, yl1, true, true, ax, S, Wf - 1, CV, codes, orow);
+                } else {
+                    const int roff[4] = {t0, b0, t1, b1};
+#pragma unroll 1
+                    for (int v = 0; v < VPT; ++v) {
+                        unsigned long long c1[1];
+                        argmax_bin_row<4, true, 1, T>(f + v * T, roff, yl0, yl1, yv0, yv1, ax, S, Wf - 1, CV, c1, orow + v * T);
+                        codes[v] = c1[0];
+                    }
+                }
+#pragma unroll
+                for (int v = 0; v < VPT; ++v)
+                    for (int px = 0; px < P; ++px) crow[(size_t)px * CV + v * T] = (unsigned char)(codes[v] >> (px * 8));
+            } else {
+                float4* g = dfeat + (size_t)b * Hf * Wf * CV + cv;
+                const float4* gy_row = dy_in + (bin0 + (size_t)py * P) * CV + cv;
+                unsigned long long codes[VPT];
+#pragma unroll
+                for (int v = 0; v < VPT; ++v) {
+                    codes[v] = 0ull;
+                    for (int px = 0; px < P; ++px)
+                        codes[v] |= (unsigned long long)__ldg(crow + (size_t)px * CV + v * T) << (px * 8);
+                }
+                if (shape == 2) {
+                    const int roff[4] = {t0, b0, 0, 0};
+                    scatter_bin_row<2, false, VPT, T>(g, roff, yl0, yl1, true, true, ax, S, Wf - 1, CV, gy_row, codes);
+                } else if (shape == 3) {
+                    const int roff[4] = {t0, b0, b1, 0};
+                    scatter_bin_row<3, false, VPT, T>(g, roff, yl0, yl1, true, true, ax, S, Wf - 1, CV, gy_row, codes);
+                } else {
+                    const int roff[4] = {t0, b0, t1, b1};
+#pragma unroll 1
+                    for (int v = 0; v < VPT; ++v) {
+                        const unsigned long long c1[1] = {codes[v]};
+                        scatter_bin_row<4, true, 1, T>(g + v * T, roff, yl0, yl1, yv0, yv1, ax, S, Wf - 1, CV, gy_row + v * T, c1);
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int MODE>
+static int launch_codes(const float* feat, int B, int Hf, int Wf, int C, const float* rois, int R, int P, float* out,
+                        unsigned char* codes, const float* dy, float* dfeat, cudaStream_t st) {
+    const dim3 grid(R, B);
+    const int cv = C / 4;
+    if (cv % 256 == 0)
+        roi_pool_codes_kernel<2, 128, MODE><<<grid, 128, 0, st>>>((const float4*)feat, Hf, Wf, cv, (const float4*)rois, R, P,
+                                                                  (float4*)out, codes, (const float4*)dy, (float4*)dfeat);
+    else if (cv > 64)
+        roi_pool_codes_kernel<1, 128, MODE><<<grid, 128, 0, st>>>((const float4*)feat, Hf, Wf, cv, (const float4*)rois, R, P,
+                                                                  (float4*)out, codes, (const float4*)dy, (float4*)dfeat);
+    else
+        roi_pool_codes_kernel<1, 64, MODE><<<grid, 64, 0, st>>>((const float4*)feat, Hf, Wf, cv, (const float4*)rois, R, P,
+                                                                (float4*)out, codes, (const float4*)dy, (float4*)dfeat);
+    FRCNN_LAUNCH_CHECK(MODE == 0 ? "roi_pool_codes_kernel<fwd>" : "roi_pool_codes_kernel<bwd>");
+    return 0;
+}
+
 }  // namespace frcnn
 
 using namespace frcnn;
@@ -733,6 +841,34 @@ int frcnn_roi_pool_backward(const float* feat, int B, int Hf, int Wf, int C, con
                                                                                  P, k, dy, dfeat);
     FRCNN_LAUNCH_CHECK("roi_pool_bwd_kernel");
     return 0;
+}
+
+int frcnn_roi_pool_argmax_supported(int C, int pooled_size, int kernel_size) {
+    return (C % 4 == 0 && kernel_size == 2 && pooled_size >= 1 && pooled_size <= 8) ? 1 : 0;
+}
+
+int frcnn_roi_pool_forward_argmax(const float* feat, int B, int Hf, int Wf, int C, const float* rois, int R, int P, int k,
+                                  float* out, unsigned char* argmax_codes, frcnn_stream_t stream) {
+    FRCNN_REQUIRE(B > 0 && Hf > 0 && Wf > 0 && C > 0 && R >= 0 && B <= 65535, FRCNN_EINVAL, "roi_pool_forward_argmax: bad shape");
+    FRCNN_REQUIRE(frcnn_roi_pool_argmax_supported(C, P, k) && (int64_t)Hf * Wf * (C / 4) < (1ll << 31), FRCNN_ELIMIT,
+                  "roi_pool_forward_argmax: needs C %% 4 == 0, kernel_size == 2, pooled_size <= 8");
+    FRCNN_REQUIRE(aligned16(feat) && aligned16(rois) && aligned16(out) && argmax_codes, FRCNN_EINVAL,
+                  "roi_pool_forward_argmax: pointers must be 16-byte aligned");
+    if (R == 0) return 0;
+    return launch_codes<0>(feat, B, Hf, Wf, C, rois, R, P, out, argmax_codes, nullptr, nullptr, as_stream(stream));
+}
+
+int frcnn_roi_pool_backward_argmax(int B, int Hf, int Wf, int C, const float* rois, int R, int P, int k, const float* dy,
+                                   const unsigned char* argmax_codes, float* dfeat, frcnn_stream_t stream) {
+    FRCNN_REQUIRE(B > 0 && Hf > 0 && Wf > 0 && C > 0 && R >= 0 && B <= 65535, FRCNN_EINVAL, "roi_pool_backward_argmax: bad shape");
+    FRCNN_REQUIRE(frcnn_roi_pool_argmax_supported(C, P, k) && (int64_t)Hf * Wf * (C / 4) < (1ll << 31), FRCNN_ELIMIT,
+                  "roi_pool_backward_argmax: needs C %% 4 == 0, kernel_size == 2, pooled_size <= 8");
+    FRCNN_REQUIRE(aligned16(rois) && aligned16(dy) && aligned16(dfeat) && argmax_codes, FRCNN_EINVAL,
+                  "roi_pool_backward_argmax: pointers must be 16-byte aligned");
+    FRCNN_CUDA(cudaMemsetAsync(dfeat, 0, sizeof(float) * (size_t)B * Hf * Wf * C, as_stream(stream)));
+    if (R == 0) return 0;
+    return launch_codes<1>(nullptr, B, Hf, Wf, C, rois, R, P, nullptr, const_cast<unsigned char*>(argmax_codes), dy, dfeat,
+                           as_stream(stream));
 }
 
 }  // extern "C"

@@ -37,17 +37,55 @@ def roi_pool_backward(feature_maps, rois, dy, pooled_size, kernel_size):
     return df
 
 
+def roi_pool_forward_argmax(feature_maps, rois, pooled_size, kernel_size):
+    """Training-mode forward: (pooled [B,R,P,P,C], argmax codes [B,R,P,P,C/4] uint8 -- four 2-bit window positions per
+    float4 of channels).  The codes let ``roi_pool_backward_argmax`` skip the second interpolation pass."""
+    f, r = as_device(feature_maps), as_device(rois)
+    B, Hf, Wf, C = f.shape
+    R = r.shape[1]
+    P, k = int(pooled_size), int(kernel_size)
+    out = torch.empty((B, R, P, P, C), dtype=torch.float32, device=f.device)
+    codes = torch.empty((B, R, P, P, C // 4), dtype=torch.uint8, device=f.device)
+    check(lib().frcnn_roi_pool_forward_argmax(ptr(f), B, Hf, Wf, C, ptr(r), R, P, k, ptr(out), ptr(codes), stream()),
+          "roi_pool_forward_argmax")
+    return out, codes
+
+
+def roi_pool_backward_argmax(feature_shape, rois, dy, argmax_codes, pooled_size, kernel_size):
+    """Gradient w.r.t. the feature maps from saved arg-max codes (no feature maps needed)."""
+    r, g = as_device(rois), as_device(dy)
+    B, Hf, Wf, C = (int(v) for v in feature_shape)
+    R = r.shape[1]
+    P, k = int(pooled_size), int(kernel_size)
+    if g.numel() != B * R * P * P * C:
+        raise ValueError(f"dy has {g.numel()} elements, expected {B * R * P * P * C}")
+    df = torch.empty((B, Hf, Wf, C), dtype=torch.float32, device=g.device)
+    check(lib().frcnn_roi_pool_backward_argmax(B, Hf, Wf, C, ptr(r), R, P, k, ptr(g), ptr(argmax_codes), ptr(df), stream()),
+          "roi_pool_backward_argmax")
+    return df
+
+
 class _ROIPoolFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feature_maps, rois, pooled_size, kernel_size):
-        ctx.save_for_backward(feature_maps, rois)
         ctx.pk = (pooled_size, kernel_size)
+        ctx.fshape = tuple(feature_maps.shape)
+        ctx.with_codes = bool(feature_maps.requires_grad and
+                              lib().frcnn_roi_pool_argmax_supported(feature_maps.shape[-1], pooled_size, kernel_size))
+        if ctx.with_codes:  # training: remember which crop sample won each window (1 byte per float4)
+            out, codes = roi_pool_forward_argmax(feature_maps, rois, pooled_size, kernel_size)
+            ctx.save_for_backward(rois, codes)
+            return out
+        ctx.save_for_backward(feature_maps, rois)
         return roi_pool_forward(feature_maps, rois, pooled_size, kernel_size)
 
     @staticmethod
     def backward(ctx, dy):
-        feature_maps, rois = ctx.saved_tensors
         # no box gradient: the proposals are stop_gradient-ed in the reference (post_processing.py:58)
+        if ctx.with_codes:
+            rois, codes = ctx.saved_tensors
+            return roi_pool_backward_argmax(ctx.fshape, rois, dy.contiguous(), codes, *ctx.pk), None, None, None
+        feature_maps, rois = ctx.saved_tensors
         return roi_pool_backward(feature_maps, rois, dy.contiguous(), *ctx.pk), None, None, None
 
 

@@ -141,6 +141,18 @@ FRCNN_API int frcnn_roi_pool_backward(const float* feature_maps, int B, int Hf, 
                             int pooled_size, int kernel_size, const float* dy, float* dfeature,
                             frcnn_stream_t stream);
 
+/* Training-mode pair: the forward additionally writes the per-channel arg-max of every 2x2 window as 2-bit codes
+ * (argmax_codes [B,R,P,P,C/4] bytes, four codes per float4 of channels), the backward consumes them and needs neither
+ * the feature maps nor a second interpolation pass.  Same results as the two functions above.
+ * Supported when frcnn_roi_pool_argmax_supported returns 1: C % 4 == 0, kernel_size == 2, pooled_size <= 8. */
+FRCNN_API int frcnn_roi_pool_argmax_supported(int C, int pooled_size, int kernel_size);
+FRCNN_API int frcnn_roi_pool_forward_argmax(const float* feature_maps, int B, int Hf, int Wf, int C, const float* rois, int R,
+                                  int pooled_size, int kernel_size, float* out, unsigned char* argmax_codes,
+                                  frcnn_stream_t stream);
+FRCNN_API int frcnn_roi_pool_backward_argmax(int B, int Hf, int Wf, int C, const float* rois, int R, int pooled_size,
+                                   int kernel_size, const float* dy, const unsigned char* argmax_codes, float* dfeature,
+                                   frcnn_stream_t stream);
+
 /* ---- utils/training.py:7-77 generate_targets (+ :123-143), batched over images -------------
  *   gt_labels [B,G,nc+1] one-hot, zero rows = padding; gt_boxes [B,G,4] rel;
  *   regions [N,4] (regions_batched=0) or [B,N,4], abs.

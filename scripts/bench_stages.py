@@ -67,7 +67,12 @@ def main():
         dy = torch.randn((B, R, 7, 7, C), device=dev)
         ms = timeit(lambda: det.roi_pool_backward(feat, rois, dy, 7, 2), iters=10, flush=flush)
         report("roi_pool_backward", wname, ms, 4 * C * (49 * R + 3 * Hf * Wf) * B)
-        del dy
+        out_a, codes = det.roi_pool_forward_argmax(feat, rois, 7, 2)
+        ms = timeit(lambda: det.roi_pool_forward_argmax(feat, rois, 7, 2), flush=flush)
+        report("roi_pool_forward + argmax codes (training forward)", wname, ms, (4 * C * (Hf * Wf + 49 * R) + 49 * R * C // 4) * B)
+        ms = timeit(lambda: det.roi_pool_backward_argmax(feat.shape, rois, dy, codes, 7, 2), iters=10, flush=flush)
+        report("roi_pool_backward from saved argmax codes", wname, ms, (4 * C * (49 * R + 2 * Hf * Wf) + 49 * R * C // 4) * B)
+        del dy, out_a, codes
         # training path: target matching on the valid anchors (RPN) and on the proposals (RCNN)
         a_all = det.generate_anchors(w.grid, w.scales, w.aspect_ratios, w.base_anchor_shape)
         valid = a_all[det.valid_anchor_indices(a_all, w.image_shape)].contiguous()
@@ -76,7 +81,14 @@ def main():
         glt, gbt = torch.as_tensor(gl).to(dev), torch.as_tensor(gb).to(dev)
         ms = timeit(lambda: det.generate_targets_batched(obj, gbt, valid, w.image_shape, [0.7, 1.0], [0.0, 0.3]), flush=flush)
         report("generate_targets RPN (N_valid x 100)", wname, ms, 40 * valid.shape[0] * B, {"N_valid": int(valid.shape[0])})
+        # RCNN-stage postprocess (7 classes, per-class cap 100, cross-class merge to 300): SURVEY 8(f) rank 1
+        lg = torch.randn((B, R, 8), device=dev) * 1.5
+        sc7 = torch.softmax(lg, -1).contiguous()
+        dl7 = (torch.randn((B, R, 7, 4), device=dev) * 0.1).contiguous()
         rois_abs = det.to_absolute(rois, w.image_shape)
+        kw7 = dict(score_threshold=0.0, iou_threshold=0.6, max_output_size_per_class=100, max_total_size=300)
+        ms = timeit(lambda: det.postprocess_output(w.image_shape, rois_abs, sc7, dl7, **kw7), flush=flush)
+        report("postprocess_output RCNN form (7 classes)", wname, ms, B * R * 7 * 44)
         ms = timeit(lambda: det.generate_targets_batched(glt, gbt, rois_abs, w.image_shape, [0.5, 1.0], [0.0, 0.5]), flush=flush)
         report("generate_targets RCNN (R x G', 7 classes)", wname, ms, (16 + 4 * 8 + 16 * 7) * R * B)
 

@@ -255,6 +255,15 @@ def test_roi_pool_backward(det, orc, syn, rng, grid, C, R, relu):
     det.ROIPooling(7, 2)(ft, rt, True, True).backward(dev(dy).reshape(2, R, -1))
     np.testing.assert_allclose(host(ft.grad), ref, rtol=RTOL, atol=RTOL * np.abs(ref).max())
     assert rt.grad is None
+    # explicit saved-argmax pair (what autograd uses when the shape supports it) == recompute path
+    if C % 4 == 0:
+        out_a, codes = det.roi_pool_forward_argmax(dev(f), dev(rois), 7, 2)
+        np.testing.assert_array_equal(host(out_a), orc.roi_pool_forward(f, rois, 7, 2))
+        _, am = orc.roi_pool_forward(f, rois, 7, 2, return_argmax=True)  # uint8 window position per channel
+        packed = (am[..., 0::4] | (am[..., 1::4] << 2) | (am[..., 2::4] << 4) | (am[..., 3::4] << 6)).astype(np.uint8)
+        np.testing.assert_array_equal(host(codes), packed)  # first-max tie rule (T8), bit for bit
+        got2 = host(det.roi_pool_backward_argmax(f.shape, dev(rois), dev(dy), codes, 7, 2))
+        np.testing.assert_allclose(got2, ref, rtol=RTOL, atol=RTOL * np.abs(ref).max())
 
 
 # ------------------------------------------------------------------ generate_targets
