@@ -139,25 +139,33 @@ struct AxisX {             // per crop column: feature cell (left column index, 
     float lerp[kMaxCrop];
 };
 
-// Packed fp32x2 lerp a + (b - a) * w for a float4 (Blackwell FADD2 / FMUL2: two fp32 lanes per issue slot).
-// Every element still sees sub.rn, mul.rn, add.rn separately rounded, i.e. the same bits as lerpv().  The final
-// add stays scalar on purpose: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (single rounding) even
-// under -fmad=false, which would break bit parity with the reference's unfused CPU arithmetic.
+// Packed fp32x2 lerp a + (b - a) * w for a float4 (Blackwell FADD2 / FMUL2 / FFMA2: two fp32 lanes per issue slot).
+// Every element still sees sub.rn, mul.rn, add.rn SEPARATELY rounded, i.e. the same bits as lerpv() and as the
+// reference's unfused CPU arithmetic.  The catch: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (single
+// rounding) even under -fmad=false, and also folds fma(p, 1.0f, a).  So the final add is written as
+// fma.rn.f32x2(p, ONE, a) with ONE read from constant memory at run time: the compiler cannot fold it, and
+// p * 1 + a rounds exactly like p + a.
+__device__ __constant__ float kRuntimeOne = 1.0f;
+
 __device__ __forceinline__ float4 lerp_packed(const float4& a, const float4& b, float w) {
-    unsigned long long a0, a1, b0, b1, d0, d1, ww;
+    unsigned long long a0, a1, b0, b1, d0, d1, ww, one;
+    const float onef = kRuntimeOne;
     asm("mov.b64 %0, {%1,%2};" : "=l"(a0) : "f"(a.x), "f"(a.y));
     asm("mov.b64 %0, {%1,%2};" : "=l"(a1) : "f"(a.z), "f"(a.w));
     asm("mov.b64 %0, {%1,%2};" : "=l"(b0) : "f"(b.x), "f"(b.y));
     asm("mov.b64 %0, {%1,%2};" : "=l"(b1) : "f"(b.z), "f"(b.w));
     asm("mov.b64 %0, {%1,%1};" : "=l"(ww) : "f"(w));
+    asm("mov.b64 %0, {%1,%1};" : "=l"(one) : "f"(onef));
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d0) : "l"(b0), "l"(a0));
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d1) : "l"(b1), "l"(a1));
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d0) : "l"(d0), "l"(ww));
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d1) : "l"(d1), "l"(ww));
-    float p0, p1, p2, p3;
-    asm("mov.b64 {%0,%1}, %2;" : "=f"(p0), "=f"(p1) : "l"(d0));
-    asm("mov.b64 {%0,%1}, %2;" : "=f"(p2), "=f"(p3) : "l"(d1));
-    return make_float4(fadd(a.x, p0), fadd(a.y, p1), fadd(a.z, p2), fadd(a.w, p3));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d0) : "l"(d0), "l"(one), "l"(a0));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d1) : "l"(d1), "l"(one), "l"(a1));
+    float4 r;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(d0));
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(r.z), "=f"(r.w) : "l"(d1));
+    return r;
 }
 
 __device__ __forceinline__ float4 vmax4(const float4& a, const float4& b) {
