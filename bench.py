@@ -359,6 +359,16 @@ def main():
     sys.modules["_frcnn_synthetic"] = syn
     spec.loader.exec_module(syn)
     w = syn.WORKLOADS[args.workload]
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # launched plainly with --gpus N: start one rank per GPU ourselves (the driver normally does this with torchrun)
+        import socket
+        import subprocess
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
     if args.impl == "reference":
         return run_reference_arm(args, w, syn)
     return run_b200_arm(args, w, syn)
