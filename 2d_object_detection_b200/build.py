@@ -47,6 +47,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB_PATH
     cmd = [_nvcc(), *NVCC_FLAGS, "-I", INCLUDE, "-o", LIB_PATH, *sources()]
+    for d in os.environ.get("FRCNN_DEFINES", "").split():  # e.g. FRCNN_DEFINES=FRCNN_DEBUG_SPIN (bounded mbarrier waits)
+        cmd[1:1] = ["-D" + d]
     if os.path.exists("/usr/bin/g++"):
         cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
     if verbose:

@@ -7,37 +7,11 @@
 // owns one float4 of channels and walks the bins of one RoI, so every global access is a coalesced
 // 128-bit load/store.  Arithmetic follows the TF CPU kernel operation by operation with explicit _rn
 // intrinsics: the forward result is bit-identical to the CPU oracle.
-#include "common.cuh"
+#include <stdlib.h>
+
+#include "roi_axis.cuh"
 
 namespace frcnn {
-
-constexpr int kMaxCrop = 32;  // S = P*k <= 32
-constexpr int kRoiThreads = 256;
-
-struct AxisTab {
-    int lo[kMaxCrop];
-    int hi[kMaxCrop];
-    float lerp[kMaxCrop];
-    int valid[kMaxCrop];
-};
-
-// Sampling position i of crop_and_resize along one axis; op order of crop_and_resize_op.cc.
-__device__ __forceinline__ void axis_sample(float c1, float c2, int extent, int S, int i, AxisTab& t) {
-    const float em1 = (float)(extent - 1);
-    float in;
-    if (S > 1) {
-        const float scale = fdiv(fmul(fsub(c2, c1), em1), (float)(S - 1));
-        in = fadd(fmul(c1, em1), fmul((float)i, scale));
-    } else {
-        in = fmul(fmul(0.5f, fadd(c1, c2)), em1);
-    }
-    const bool ok = (in >= 0.0f) && (in <= em1);  // NaN -> not sampled
-    t.valid[i] = ok ? 1 : 0;
-    const float fl = ok ? floorf(in) : 0.0f;
-    t.lo[i] = (int)fl;
-    t.hi[i] = ok ? (int)ceilf(in) : 0;
-    t.lerp[i] = ok ? fsub(in, fl) : 0.0f;
-}
 
 // ---- tiny vector abstraction: float4 (C % 4 == 0) or float -------------------------------------
 __device__ __forceinline__ float4 vload(const float4* p) { return __ldg(p); }
@@ -797,6 +771,9 @@ int frcnn_roi_pool_forward(const float* feat, int B, int Hf, int Wf, int C, cons
     FRCNN_REQUIRE(B <= 65535, FRCNN_ELIMIT, "roi_pool_forward: B > 65535");
     if (R == 0) return 0;
     const dim3 grid(R, B);
+    static const bool use_stream = getenv("FRCNN_FWD_STREAM") != nullptr;  // experimental row-streaming kernel (A/B switch)
+    if (roi_pool_stream_supported(C, P, k) && use_stream)
+        return launch_roi_pool_fwd_stream(feat, B, Hf, Wf, C, rois, R, out, as_stream(stream));
     if (C % 4 == 0 && k == 2 && (int64_t)Hf * Wf * (C / 4) < (1ll << 31)) {
         const int cv = C / 4;
         if (cv % 256 == 0)
