@@ -1,24 +1,27 @@
 // Row-streaming RoI pooling forward for the reference configuration (pooled_size 7, kernel_size 2: a 14 x 14
 // crop_and_resize max-pooled 2 x 2; models/detectors/fast_rcnn_detector.py:134-177).
 //
-// CTA = one RoI x 512 channels, 256 threads, one float2 of channels per thread (128 registers, 2 CTAs per SM).
-//   * Prologue (warp 0, registers + shuffles): the 14 x-samples of the RoI touch at most 28 distinct feature columns;
-//     they are compacted into a sorted list (match_any + rank).  The 14 y-samples become a short program: per crop
-//     row which of the two register row sets must be (re)loaded and which one holds the top row, plus the list of
-//     feature rows the downward walk needs, in order.
-//   * Staging: a feature row is brought in with ONE cp.async.bulk per distinct column (TMA engine, 2 KB = 512 channels
-//     of one pixel, issued lane-parallel by one warp) into slot `k % depth` of a shared-memory ring; a "full" mbarrier
-//     per slot carries the byte count.  The ring depth adapts to the RoI: narrow RoIs (few columns, small slots) get a
-//     deep ring.  There is no producer warp: the LAST warp to finish reading a slot (shared-memory arrival counter)
-//     refills it at once with the row `depth` further down, so nobody ever waits for a slot to drain.
+// CTA = one RoI x 512 channels, 8 warps; a warp owns 64 channels (one float2 per lane; 128 registers, 2 CTAs per SM)
+// and runs its OWN copy pipeline -- after the prologue the warps never synchronise with each other.
+//   * Prologue (warp 0, registers + shuffles): the feature columns [cmin, cmax] under the 14 x-samples select one of
+//     eight TMA tensor maps (box = 64 channels x W pixels, W >= the span); the 14 y-samples become the list of feature
+//     rows the downward walk needs, in order, and per crop row the walk position that completes it.
+//   * Staging: ONE cp.async.bulk.tensor per feature row and warp (box of W consecutive pixels x 64 channels of the
+//     [B*Hf*Wf, C] view of the NHWC maps) into slot `k % depth` of the warp's private shared-memory ring, completion
+//     on the slot's mbarrier.  The ring depth adapts to the RoI: narrow RoIs (small boxes) get a deep ring.  When a
+//     warp has consumed row k it immediately re-arms the slot with row k + depth -- no producer warp, no hand-shake.
 //   * A staged row is x-interpolated ONCE at all 14 sample positions into one of two register row sets (operands from
-//     shared memory, addresses from a 14-entry table); the sets alternate as top / bottom neighbour while the walk
-//     moves down; each crop row is then 14 y-interpolations folded straight into the 7 running bin maxima, stored
-//     after every second crop row.  All control flow is CTA-uniform, every register index is static.
+//     shared memory, addresses from a 14-entry table).  Walk position k lands in set k & 1, so the newest row is
+//     always the bottom neighbour; each finished crop row is 14 y-interpolations folded straight into the 7 running
+//     bin maxima, stored after every second crop row.  All control flow is CTA-uniform, every register index static.
 // Per sample the fp32 operations and their order are those of TF's CPU kernel (t = TL + (TR - TL) * xl, b likewise,
 // out = t + (b - t) * yl, each op rounded separately; packed FADD2/FMUL2/FFMA2 with a run-time 1.0, see lerp2):
 // results are bit-identical to the oracle.  Compared with the bin-row walk (roi_pool.cu) every feature pixel is read
 // from L2 once per RoI instead of once per bin-row, a row is x-interpolated once per RoI, and nobody waits on L2.
+// RoIs whose x-samples span more than 51 feature columns do not fit the ring; they take a plain gather path.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include "roi_axis.cuh"
 
 namespace frcnn {
@@ -28,36 +31,39 @@ namespace {
 constexpr int kS = 14;                         // crop size = pooled_size * kernel_size
 constexpr int kP = 7;
 constexpr int kChunk = 512;                    // channels per CTA
-constexpr int kThreads = kChunk / 2;           // one float2 of channels per thread; 8 warps
-constexpr int kWarps = kThreads / 32;
-constexpr int kPixBytes = kChunk * 4;          // one pixel's channel chunk
-constexpr int kRingPix = 52;                   // 104 KB ring: depth(28 columns) = 1, (25) = 2, (16) = 3, (12) = 4
-constexpr int kRingBytes = kRingPix * kPixBytes;
+constexpr int kWarpCh = 64;                    // channels per warp: one float2 per lane
+constexpr int kWarps = kChunk / kWarpCh;
+constexpr int kThreads = kWarps * 32;
+constexpr int kPixBytes = kWarpCh * 4;         // one pixel in a warp's ring
+constexpr int kRingPix = 52;                   // pixels per warp ring: 8 warps x 52 x 256 B = 104 KB per CTA
+constexpr int kWarpRingBytes = kRingPix * kPixBytes;
+constexpr int kRingBytes = kWarps * kWarpRingBytes;
 constexpr int kMaxDepth = 8;
+constexpr int kNumBoxes = 8;
+// box widths: the smallest W with floor(52 / W) = 8, 7, 6, 5, 4, 3, 2, 1 slots
+__host__ __device__ constexpr int box_width(int i) {
+    return i == 0 ? 6 : i == 1 ? 7 : i == 2 ? 8 : i == 3 ? 10 : i == 4 ? 13 : i == 5 ? 17 : i == 6 ? 26 : 52;
+}
 
 constexpr int kPosBefore = -1;  // crop row outside the map, emitted before the first staged row ...
 constexpr int kPosAfter = 99;   // ... or after the last one
+
+struct TensorMaps {
+    CUtensorMap box[kNumBoxes];
+};
 
 struct StreamShared {
     int4 xt[kS];          // per crop column: {left pixel byte offset in a slot, 0, x_lerp bits, x_lerp bits}
     int pos[kS];          // per crop row: walk position of its bottom feature row (the row whose arrival completes it)
     float ylerp[kS];
     int rows[2 * kS];     // feature rows in the order the walk consumes them
-    int cols[32];         // sorted distinct feature columns (compact index -> column)
-    int n_rows, ncols, depth, slot_bytes, first_px, spare_px;
-    int done[kMaxDepth];  // warps that have finished reading the slot's current row
-    unsigned long long full[kMaxDepth];
+    int n_rows, box, cmin, depth, slot_bytes, first_px, wide;
+    int xlo[kS], xhi[kS], xok[kS], ylo[kS], yhi[kS], yok[kS];  // plain sample tables, used by the wide-RoI path only
+    float xlerp[kS];
+    unsigned long long full[kWarps][kMaxDepth];
 };
 
 __device__ __constant__ float kOne = 1.0f;
-#ifdef FRCNN_DEBUG_SPIN
-__device__ int g_dbg[8 + 16 * 8];
-#define g_dbg_k 0
-__device__ volatile int* g_trace = nullptr;
-#define TRACE(v) do { if (g_trace && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0) { g_trace[threadIdx.x >> 5] = (v); __threadfence_system(); } } while (0)
-#else
-#define TRACE(v) do {} while (0)
-#endif
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -67,32 +73,6 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-#ifdef FRCNN_DEBUG_SPIN
-    unsigned long long t0;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    for (;;) {  // debug build: a wait that does not complete within 20 ms is recorded and the thread exits
-        unsigned ok;
-        asm volatile(
-            "{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (ok) return;
-        unsigned long long t1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 20000000ull) {
-            const int n = atomicAdd(&g_dbg[0], 1);
-            if (n < 15) {
-                int* d = g_dbg + 8 + n * 8;
-                d[0] = blockIdx.x; d[1] = blockIdx.y; d[2] = threadIdx.x; d[3] = (int)bar; d[4] = (int)parity;
-                unsigned long long st;
-                asm volatile("ld.shared.b64 %0, [%1];" : "=l"(st) : "r"(bar));
-                d[5] = (int)(st >> 32); d[6] = (int)st; d[7] = g_dbg_k;
-            }
-            asm volatile("exit;");
-        }
-    }
-#else
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -104,12 +84,13 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
         "}\n" ::"r"(bar),
         "r"(parity)
         : "memory");
-#endif
 }
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
+// box (c0 = first channel, c1 = first pixel) of the [pixels, channels] view -> shared memory, completion on `bar`
+__device__ __forceinline__ void tma_box_g2s(unsigned dst, const CUtensorMap* map, int c0, int c1, unsigned bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
 }
 
 typedef unsigned long long u64;  // two packed fp32 channels
@@ -154,50 +135,66 @@ __device__ __forceinline__ Sample sample_axis(float c1, float c2, int extent, in
     return s;
 }
 
+// Feature columns the 14 x-samples of an RoI need (full warp; lanes 0..13 hold the samples).  The right neighbour of a
+// sample is read one pixel after the left one even at an integer position (weight exactly 0), so a sample sitting
+// exactly on the last needed column asks for one more pixel (real data of the map, or TMA zero fill past its end).
+struct Span {
+    int cmin, need;  // first column, pixels to stage (0: no sample inside the map)
+    bool any_outside;
+};
+__device__ __forceinline__ Span column_span(const Sample& xs, int lane) {
+    const unsigned all = 0xffffffffu;
+    const bool ok = lane < kS && xs.ok;
+    const int cmin = __reduce_min_sync(all, ok ? xs.lo : 0x7fffffff);
+    const int cmax = __reduce_max_sync(all, ok ? xs.hi : -1);
+    const bool spare = __any_sync(all, ok && xs.hi == xs.lo && xs.lo == cmax) != 0;
+    Span s;
+    s.cmin = cmin;
+    s.need = cmax < 0 ? 0 : cmax - cmin + 1 + (spare ? 1 : 0);
+    s.any_outside = __any_sync(all, lane < kS && !xs.ok) != 0;
+    return s;
+}
+
 struct Walk {
     StreamShared* sh;
-    const unsigned char* ring;  // this thread's channels inside pixel 0 of slot 0
-    const float* src;           // staging duty: this lane's feature column (row 0) of the image, channel chunk ch0
-    size_t row_stride;          // floats per feature row
-    unsigned dst;               // staging duty: shared address of this lane's pixel in slot 0
-    unsigned full0;             // shared address of full[0]
-    int k, n_rows, ncols, depth, slot_bytes, slot;
+    const unsigned char* ring;  // this lane's channels inside pixel 0 of slot 0 of the warp's ring
+    const CUtensorMap* map;
+    unsigned dst;               // shared address where a staged box starts in slot 0 (after the optional zero pixel)
+    unsigned full0;             // shared address of this warp's full[0]
+    unsigned box_bytes;
+    int ch, pix0;               // TMA coordinates: first channel of the warp, pixel index of (row 0, cmin) of the image
+    int Wf;
+    int k, n_rows, depth, slot_bytes, slot;
     unsigned phase;
     u64 one;
 };
 
-// Stage feature row rows[idx] into `slot` (one 2 KB bulk copy per lane = per distinct column); warp-collective.
+// Stage feature row rows[idx] of the walk into `slot` of the warp's ring: one TMA box, issued by lane 0.
 __device__ __forceinline__ void stage_row(const Walk& w, int idx, int slot) {
-    const int lane = threadIdx.x & 31;
-    const unsigned bar = w.full0 + slot * 8;
-    if (lane == 0) mbar_expect_tx(bar, (unsigned)(w.ncols * kPixBytes));
-    __syncwarp();
-    if (lane < w.ncols) bulk_g2s(w.dst + slot * w.slot_bytes, w.src + w.sh->rows[idx] * w.row_stride, kPixBytes, bar);
+    if ((threadIdx.x & 31) == 0) {
+        const unsigned bar = w.full0 + slot * 8;
+        mbar_expect_tx(bar, w.box_bytes);
+        tma_box_g2s(w.dst + slot * w.slot_bytes, w.map, w.ch, w.pix0 + w.sh->rows[idx] * w.Wf, bar);
+    }
 }
 
-// x-interpolate the next staged feature row (row k of the walk) at the 14 sample positions.
+// x-interpolate the next staged feature row (row k of the walk) at the 14 sample positions, then re-arm its slot.
 __device__ __forceinline__ void load_row(Walk& w, u64 (&X)[kS]) {
-    TRACE(1000 + w.k);
     mbar_wait(w.full0 + w.slot * 8, w.phase);
-    TRACE(2000 + w.k);
     const unsigned char* base = w.ring + w.slot * w.slot_bytes;
 #pragma unroll
     for (int i = 0; i < kS; ++i) {
         const int4 e = w.sh->xt[i];
         const u64 l = *reinterpret_cast<const u64*>(base + e.x);
-        const u64 r = *reinterpret_cast<const u64*>(base + e.x + kPixBytes);  // the right neighbour is the next slot pixel
+#ifdef FRCNN_EXP_NO_R
+        const u64 r = l ^ 0x0000000100000001ull;
+#else
+        const u64 r = *reinterpret_cast<const u64*>(base + e.x + kPixBytes);  // the right neighbour is the next pixel
+#endif
         X[i] = lerp2(l, r, pack2(__int_as_float(e.z), __int_as_float(e.w)), w.one);
     }
-    // the last warp to finish with this slot refills it with the row `depth` further down the walk
-    int old = 0;
-    if ((threadIdx.x & 31) == 0) old = atomicAdd(&w.sh->done[w.slot], 1);
-    old = __shfl_sync(0xffffffffu, old, 0);
-    TRACE(3000 + w.k + 100 * old);
-    if (old == kWarps - 1) {
-        if ((threadIdx.x & 31) == 0) w.sh->done[w.slot] = 0;
-        if (w.k + w.depth < w.n_rows) stage_row(w, w.k + w.depth, w.slot);
-    }
-    TRACE(4000 + w.k);
+    __syncwarp();  // every lane has consumed its operands: the slot may be overwritten
+    if (w.k + w.depth < w.n_rows) stage_row(w, w.k + w.depth, w.slot);
     ++w.k;
     if (++w.slot == w.depth) {
         w.slot = 0;
@@ -223,55 +220,46 @@ __device__ __forceinline__ void crop_row(const u64 (&T)[kS], const u64 (&Bm)[kS]
 }
 
 __global__ void __launch_bounds__(kThreads, 2)
-    roi_pool_fwd_stream_kernel(const float* __restrict__ feat, int Hf, int Wf, int C, const float4* __restrict__ rois, int R,
-                               int nchunk, float* __restrict__ out) {
+    roi_pool_fwd_stream_kernel(const __grid_constant__ TensorMaps maps, const float* __restrict__ feat, int Hf, int Wf, int C,
+                               const float4* __restrict__ rois, int R, int nchunk, float* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char smem[];
     StreamShared& sh = *reinterpret_cast<StreamShared*>(smem);
     unsigned char* ring = smem + (sizeof(StreamShared) + 127) / 128 * 128;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int r = blockIdx.x / nchunk, ch0 = (blockIdx.x % nchunk) * kChunk, b = blockIdx.y;
-    const unsigned full0 = smem_u32(&sh.full[0]);
-    TRACE(7);
+    const unsigned full_base = smem_u32(&sh.full[0][0]);
 
     if (tid < 32) {
         const float4 roi = rois[(size_t)b * R + r];  // x1,y1,x2,y2 (fast_rcnn_detector.py:157-158 reorders for TF)
         const unsigned all = 0xffffffffu;
         const Sample xs = sample_axis(roi.x, roi.z, Wf, lane);  // lanes 0..13 are the crop columns / rows
         const Sample ys = sample_axis(roi.y, roi.w, Hf, lane);
-        // ---- columns: the distinct feature columns under the 14 x-samples -> sorted compact list; a slot holds them
-        // in that order.  The right neighbour of a sample (ceil) is the next list entry, or -- at an integer position,
-        // where its weight is exactly 0 -- whatever follows: that must be finite, so a zeroed spare pixel closes the
-        // slot when the last column can be hit that way.  A sample outside the map reads a zeroed pixel in front of
-        // the slot: 0 + (p - 0) * 0.
-        const int i = lane >> 1;
-        const int ok_i = __shfl_sync(all, (int)xs.ok, i);  // (collectives first: no short-circuit around a shuffle)
-        const bool ok = lane < 2 * kS && ok_i != 0;
-        const int lo_i = __shfl_sync(all, xs.lo, i), hi_i = __shfl_sync(all, xs.hi, i);
-        const int lerp_i = __shfl_sync(all, __float_as_int(xs.lerp), i);
-        const int val = ok ? ((lane & 1) ? hi_i : lo_i) : 0x7fffffff;
-        const unsigned same = __match_any_sync(all, val);
-        const bool leader = ok && (__ffs(same) - 1 == lane);
-        int rank = 0;
+        // ---- columns: a slot holds the pixels cmin .. cmin + W - 1 of one feature row; a sample outside the map reads
+        // a zeroed pixel in front of them: 0 + (p - 0) * 0.
+        const Span sp = column_span(xs, lane);
+        const int first_px = sp.any_outside ? 1 : 0;
+        int box = 0;
 #pragma unroll
-        for (int j = 0; j < 2 * kS; ++j) {
-            const int vj = __shfl_sync(all, val, j);
-            const int lj = __shfl_sync(all, (int)leader, j);
-            rank += (lj && vj < val) ? 1 : 0;
+        for (int i = 0; i < kNumBoxes; ++i) box += (sp.need > box_width(i)) ? 1 : 0;
+        int W = 0;
+#pragma unroll
+        for (int i = 0; i < kNumBoxes; ++i) W = (box == i) ? box_width(i) : W;
+        const bool wide = box >= kNumBoxes || W + first_px > kRingPix;  // does not fit the ring: plain gather path below
+        if (wide && lane < kS) {
+            sh.xlo[lane] = xs.lo; sh.xhi[lane] = xs.hi; sh.xok[lane] = xs.ok; sh.xlerp[lane] = xs.lerp;
+            sh.ylo[lane] = ys.lo; sh.yhi[lane] = ys.hi; sh.yok[lane] = ys.ok;
         }
-        TRACE(8);
-        const int ncols = __popc(__ballot_sync(all, leader));
-        const bool even = lane < 2 * kS && !(lane & 1);
-        const int first_px = __any_sync(all, even && !ok) ? 1 : 0;
-        const int spare_px = __any_sync(all, even && ok && hi_i == lo_i && rank == ncols - 1) ? 1 : 0;
-        if (leader) sh.cols[rank] = val;
-        if (even) sh.xt[i] = make_int4(ok ? (rank + first_px) * kPixBytes : 0, 0, ok ? lerp_i : 0, ok ? lerp_i : 0);
+        if (lane < kS) {
+            const int lerp = xs.ok ? __float_as_int(xs.lerp) : 0;
+            sh.xt[lane] = make_int4(xs.ok ? (xs.lo - sp.cmin + first_px) * kPixBytes : 0, 0, lerp, lerp);
+        }
         // ---- rows: the downward walk.  The walk stages feature rows in the order rows[0], rows[1], ...; position k
         // goes to register row set k & 1, so the most recently staged row is always the bottom neighbour and the set
         // it replaces held the old top row.  A crop row is complete when the row at pos[sy] has arrived.
-        const bool anyx = ncols > 0;
+        const bool anyx = sp.need > 0;
         const bool v = lane < kS && ys.ok && anyx;
         const int c = ys.lo;
-        const int pv_i = __shfl_up_sync(all, (int)v, 1);
+        const int pv_i = __shfl_up_sync(all, (int)v, 1);  // (collectives first: no short-circuit around a shuffle)
         const bool pv = pv_i != 0 && lane > 0;
         const int pc = __shfl_up_sync(all, c, 1);
         const bool reuse = v && pv && c == pc;          // same two feature rows as the previous crop row
@@ -293,40 +281,63 @@ __global__ void __launch_bounds__(kThreads, 2)
             sh.ylerp[lane] = ys.lerp;
         }
         if (lane == 0) {
-            const int px = ncols + first_px + spare_px;
+            const int px = W + first_px;
             sh.n_rows = __popc(m1) + __popc(m2);
-            sh.ncols = ncols;
+            sh.box = box;
+            sh.cmin = sp.cmin;
             sh.first_px = first_px;
-            sh.spare_px = spare_px;
+            sh.wide = wide ? 1 : 0;
             sh.slot_bytes = px * kPixBytes;
-            sh.depth = px ? min(kMaxDepth, kRingPix / px) : 1;
+            sh.depth = max(1, min(kMaxDepth, kRingPix / max(px, 1)));
         }
-        TRACE(9);
-    } else if (tid < 32 + kMaxDepth) {
-        mbar_init(full0 + (tid - 32) * 8, 1);
-        sh.done[tid - 32] = 0;
+    } else if (tid < 32 + kWarps * kMaxDepth) {
+        mbar_init(full_base + (tid - 32) * 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-
-#ifdef FRCNN_DEBUG_SPIN
-    if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
-        g_dbg[1] = sh.n_rows; g_dbg[2] = sh.ncols; g_dbg[3] = sh.depth; g_dbg[4] = sh.slot_bytes; g_dbg[5] = sh.first_px;
-        g_dbg[6] = sh.spare_px; g_dbg[7] = (int)full0;
+    if (sh.wide) {  // rare (x-samples more than 51 columns apart): one bilinear gather per sample, same arithmetic
+        const float onef = kOne;
+        const u64 one = pack2(onef, onef);
+        const float* fb = feat + (size_t)b * Hf * Wf * C + ch0 + tid * 2;
+        float2* ob = reinterpret_cast<float2*>(out + ((size_t)b * R + r) * (kP * kP) * C + ch0) + tid;
+#pragma unroll 1
+        for (int bin = 0; bin < kP * kP; ++bin) {
+            const int py = bin / kP, px = bin - py * kP;
+            float2 best = make_float2(0.0f, 0.0f);
+#pragma unroll 1
+            for (int s4 = 0; s4 < 4; ++s4) {
+                const int sy = 2 * py + (s4 >> 1), sx = 2 * px + (s4 & 1);
+                float2 val = make_float2(0.0f, 0.0f);  // extrapolation value
+                if (sh.yok[sy] && sh.xok[sx]) {
+                    const float* top = fb + (size_t)sh.ylo[sy] * Wf * C;
+                    const float* bot = fb + (size_t)sh.yhi[sy] * Wf * C;
+                    const size_t xl = (size_t)sh.xlo[sx] * C, xh = (size_t)sh.xhi[sx] * C;
+                    const u64 tl = *reinterpret_cast<const u64*>(top + xl), tr = *reinterpret_cast<const u64*>(top + xh);
+                    const u64 bl = *reinterpret_cast<const u64*>(bot + xl), br = *reinterpret_cast<const u64*>(bot + xh);
+                    const u64 wx = pack2(sh.xlerp[sx], sh.xlerp[sx]), wy = pack2(sh.ylerp[sy], sh.ylerp[sy]);
+                    val = unpack2(lerp2(lerp2(tl, tr, wx, one), lerp2(bl, br, wx, one), wy, one));
+                }
+                best.x = s4 == 0 ? val.x : fmaxf(best.x, val.x);
+                best.y = s4 == 0 ? val.y : fmaxf(best.y, val.y);
+            }
+            __stcs(ob + (size_t)bin * (C / 2), best);
+        }
+        return;
     }
-#endif
-    TRACE(1);
+
     Walk w;
     w.sh = &sh;
-    w.full0 = full0;
-    w.ncols = sh.ncols;
+    w.full0 = full_base + warp * (kMaxDepth * 8);
     w.n_rows = sh.n_rows;
     w.depth = sh.depth;
     w.slot_bytes = sh.slot_bytes;
-    w.row_stride = (size_t)Wf * C;
-    w.src = feat + ((size_t)b * Hf * Wf + (lane < w.ncols ? sh.cols[lane] : 0)) * C + ch0;
-    w.dst = smem_u32(ring) + (lane + sh.first_px) * kPixBytes;
-    w.ring = ring + tid * 8;
+    w.map = &maps.box[sh.box];
+    w.box_bytes = (unsigned)((sh.slot_bytes / kPixBytes - sh.first_px) * kPixBytes);
+    w.ch = ch0 + warp * kWarpCh;
+    w.pix0 = b * Hf * Wf + sh.cmin;
+    w.Wf = Wf;
+    w.dst = smem_u32(ring) + warp * kWarpRingBytes + sh.first_px * kPixBytes;
+    w.ring = ring + warp * kWarpRingBytes + lane * 8;
     w.k = 0;
     w.slot = 0;
     w.phase = 0;
@@ -335,18 +346,11 @@ __global__ void __launch_bounds__(kThreads, 2)
         w.one = pack2(onef, onef);
     }
     if (w.n_rows > 0) {
-        if (tid < 32)
-            for (int s = 0; s < w.depth && s < w.n_rows; ++s) stage_row(w, s, s);
-        TRACE(2);
-        // zero pixels of every slot (each thread later reads only what it wrote itself)
-        for (int s = 0; s < w.depth; ++s) {
-            unsigned char* slot0 = ring + s * w.slot_bytes + tid * 8;
-            if (sh.first_px) *reinterpret_cast<u64*>(slot0) = 0ull;
-            if (sh.spare_px) *reinterpret_cast<u64*>(slot0 + (sh.first_px + w.ncols) * kPixBytes) = 0ull;
-        }
+        for (int s = 0; s < w.depth && s < w.n_rows; ++s) stage_row(w, s, s);
+        if (sh.first_px)  // the zero pixel of every slot (each lane later reads only what it wrote itself)
+            for (int s = 0; s < w.depth; ++s) *reinterpret_cast<u64*>(const_cast<unsigned char*>(w.ring) + s * w.slot_bytes) = 0ull;
     }
 
-    TRACE(3);
     u64 X0[kS], X1[kS];
 #pragma unroll
     for (int i = 0; i < kS; ++i) X0[i] = X1[i] = 0ull;
@@ -390,23 +394,59 @@ __global__ void __launch_bounds__(kThreads, 2)
         }
     }
     while (sy < kS) emit(X0, X1, true);
-    TRACE(9999);
+}
+
+// Host side: the eight tensor maps of a feature tensor, cached by (pointer, shape).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct MapCacheEntry {
+    const void* ptr = nullptr;
+    long long pixels = 0;
+    int C = 0, dev = -1;
+    TensorMaps maps;
+};
+
+int get_tensor_maps(const float* feat, long long pixels, int C, int dev, const TensorMaps** out) {
+    static thread_local MapCacheEntry cache[16];
+    static thread_local int next = 0;
+    static EncodeTiledFn encode = nullptr;
+    for (auto& e : cache)
+        if (e.ptr == feat && e.pixels == pixels && e.C == C && e.dev == dev) {
+            *out = &e.maps;
+            return 0;
+        }
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        FRCNN_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        FRCNN_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, FRCNN_EINVAL,
+                      "roi_pool_forward: cuTensorMapEncodeTiled not available in this driver");
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    MapCacheEntry& e = cache[next];
+    next = (next + 1) % 16;
+    e.ptr = nullptr;
+    for (int i = 0; i < kNumBoxes; ++i) {
+        const cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)pixels};
+        const cuuint64_t strides[1] = {(cuuint64_t)C * sizeof(float)};
+        const cuuint32_t box[2] = {(cuuint32_t)kWarpCh, (cuuint32_t)box_width(i)};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult cr = encode(&e.maps.box[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(feat), dims, strides,
+                                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        FRCNN_REQUIRE(cr == CUDA_SUCCESS, FRCNN_EINVAL, "roi_pool_forward: cuTensorMapEncodeTiled failed (CUresult %d)", (int)cr);
+    }
+    e.ptr = feat;
+    e.pixels = pixels;
+    e.C = C;
+    e.dev = dev;
+    *out = &e.maps;
+    return 0;
 }
 
 }  // namespace
-
-#ifdef FRCNN_DEBUG_SPIN
-extern "C" __attribute__((visibility("default"))) int frcnn_debug_set_trace(int* mapped) {
-    return (int)cudaMemcpyToSymbol(g_trace, &mapped, sizeof(mapped));
-}
-extern "C" __attribute__((visibility("default"))) int frcnn_debug_read(int* host_dst) {
-    cudaDeviceSynchronize();
-    int z[8 + 16 * 8] = {};
-    cudaError_t e = cudaMemcpyFromSymbol(host_dst, g_dbg, sizeof(z));
-    cudaMemcpyToSymbol(g_dbg, z, sizeof(z));
-    return (int)e;
-}
-#endif
 
 bool roi_pool_stream_supported(int C, int P, int k) { return C % kChunk == 0 && P == kP && k == 2; }
 
@@ -422,8 +462,12 @@ int launch_roi_pool_fwd_stream(const float* feat, int B, int Hf, int Wf, int C, 
     }
     const int nchunk = C / kChunk;
     FRCNN_REQUIRE((int64_t)R * nchunk < (1ll << 31), FRCNN_ELIMIT, "roi_pool_forward: R * C / 512 too large");
+    FRCNN_REQUIRE((int64_t)B * Hf * Wf < (1ll << 31), FRCNN_ELIMIT, "roi_pool_forward: B * Hf * Wf too large");
+    const TensorMaps* maps = nullptr;
+    const int rc = get_tensor_maps(feat, (long long)B * Hf * Wf, C, dev, &maps);
+    if (rc) return rc;
     const dim3 grid(R * nchunk, B);
-    roi_pool_fwd_stream_kernel<<<grid, kThreads, smem, st>>>(feat, Hf, Wf, C, (const float4*)rois, R, nchunk, out);
+    roi_pool_fwd_stream_kernel<<<grid, kThreads, smem, st>>>(*maps, feat, Hf, Wf, C, (const float4*)rois, R, nchunk, out);
     FRCNN_LAUNCH_CHECK("roi_pool_fwd_stream_kernel");
     return 0;
 }

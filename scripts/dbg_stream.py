@@ -1,16 +1,15 @@
-import sys, importlib, ctypes, time, os, numpy as np, torch
-sys.path.insert(0,'/root/repo')
+"""Quick check of the row-streaming RoI forward against the oracle (run with FRCNN_FWD_STREAM=1)."""
+import sys, importlib, os, numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 det = importlib.import_module('2d_object_detection_b200'); syn = det.synthetic
+import oracle
 rng = np.random.default_rng(0)
-L = ctypes.CDLL('/root/repo/2d_object_detection_b200/libfrcnn_b200.so')
-trace = torch.zeros(64, dtype=torch.int32).pin_memory()
-print('set trace', L.frcnn_debug_set_trace(ctypes.c_void_p(trace.data_ptr())), flush=True)
-grid, C, R = (24, 78), 1024, 40
-f = syn.feature_maps(rng, 2, grid, C, relu=True)
-rois = syn.random_rois(rng, 2, R, num_valid=[R-2,R]); rois[1,0]=[0.25,0.1,1.0,1.0]
-ft = torch.as_tensor(f).cuda(); rt = torch.as_tensor(rois[:, 0:1].copy()).cuda(); torch.cuda.synchronize()
-out = det.roi_pool_forward(ft, rt, 7, 2)
-time.sleep(2.0)
-print('trace', trace[:8].tolist(), flush=True)
-buf = (ctypes.c_int * 136)()
-os._exit(0)
+for grid, C, R in [((24, 78), 1024, 40), ((9, 11), 512, 8), ((50, 84), 512, 30), ((3, 2), 512, 6)]:
+    f = syn.feature_maps(rng, 2, grid, C, relu=True)
+    rois = syn.random_rois(rng, 2, R, num_valid=[R - 2, R]); rois[1, 0] = [0.25, 0.1, 1.0, 1.0]
+    rois[1, 1] = [0.0, 0.0, 1.0, 1.0]; rois[1, 2] = [0.9, 0.8, 0.1, 0.2]; rois[1, 3] = [-0.2, 0.3, 0.4, 1.3]; rois[0, 0] = [0.02, 0.0, 0.97, 0.5]
+    out = det.roi_pool_forward(torch.as_tensor(f).cuda(), torch.as_tensor(rois).cuda(), 7, 2); torch.cuda.synchronize()
+    ref = oracle.roi_pool_forward(f, rois, 7, 2)
+    got = out.cpu().numpy()
+    bad = [(b, r) for b in range(2) for r in range(R) if not np.array_equal(got[b, r], ref[b, r])]
+    print(grid, C, 'ok' if not bad else ('MISMATCH', bad[:10]), flush=True)
