@@ -771,8 +771,8 @@ int frcnn_roi_pool_forward(const float* feat, int B, int Hf, int Wf, int C, cons
     FRCNN_REQUIRE(B <= 65535, FRCNN_ELIMIT, "roi_pool_forward: B > 65535");
     if (R == 0) return 0;
     const dim3 grid(R, B);
-    static const bool use_stream = getenv("FRCNN_FWD_STREAM") != nullptr;  // experimental row-streaming kernel (A/B switch)
-    if (roi_pool_stream_supported(C, P, k) && use_stream)
+    static const bool force_walk = getenv("FRCNN_FWD_WALK") != nullptr;  // A/B switch for benchmarking the older bin-row walk
+    if (roi_pool_stream_supported(C, P, k) && !force_walk)
         return launch_roi_pool_fwd_stream(feat, B, Hf, Wf, C, rois, R, out, as_stream(stream));
     if (C % 4 == 0 && k == 2 && (int64_t)Hf * Wf * (C / 4) < (1ll << 31)) {
         const int cv = C / 4;

@@ -45,8 +45,6 @@ __host__ __device__ constexpr int box_width(int i) {
     return i == 0 ? 6 : i == 1 ? 7 : i == 2 ? 8 : i == 3 ? 10 : i == 4 ? 13 : i == 5 ? 17 : i == 6 ? 26 : 52;
 }
 
-constexpr int kPosBefore = -1;  // crop row outside the map, emitted before the first staged row ...
-constexpr int kPosAfter = 99;   // ... or after the last one
 
 struct TensorMaps {
     CUtensorMap box[kNumBoxes];
@@ -54,10 +52,12 @@ struct TensorMaps {
 
 struct StreamShared {
     int4 xt[kS];          // per crop column: {left pixel byte offset in a slot, 0, x_lerp bits, x_lerp bits}
-    int pos[kS];          // per crop row: walk position of its bottom feature row (the row whose arrival completes it)
     float ylerp[kS];
     int rows[2 * kS];     // feature rows in the order the walk consumes them
     int n_rows, box, cmin, depth, slot_bytes, first_px, wide;
+    unsigned prog_lo, prog_hi;  // the walk as a bit string, consumed LSB first: 0 = stage-and-interpolate the next feature
+                                // row, 1 = the next crop row is complete (both its rows are in registers): emit it
+    int n_before, n_after;      // crop rows outside the map before / after the rows inside it
     int xlo[kS], xhi[kS], xok[kS], ylo[kS], yhi[kS], yok[kS];  // plain sample tables, used by the wide-RoI path only
     float xlerp[kS];
     unsigned long long full[kWarps][kMaxDepth];
@@ -159,45 +159,45 @@ struct Walk {
     StreamShared* sh;
     const unsigned char* ring;  // this lane's channels inside pixel 0 of slot 0 of the warp's ring
     const CUtensorMap* map;
-    unsigned dst;               // shared address where a staged box starts in slot 0 (after the optional zero pixel)
     unsigned full0;             // shared address of this warp's full[0]
-    unsigned box_bytes;
-    int ch, pix0;               // TMA coordinates: first channel of the warp, pixel index of (row 0, cmin) of the image
-    int Wf;
-    int k, n_rows, depth, slot_bytes, slot;
+    int k, n_rows, depth, slot_bytes, slot, slot_off;
     unsigned phase;
     u64 one;
 };
 
-// Stage feature row rows[idx] of the walk into `slot` of the warp's ring: one TMA box, issued by lane 0.
-__device__ __forceinline__ void stage_row(const Walk& w, int idx, int slot) {
+// Stage feature row rows[idx] of the walk into the slot at byte offset slot_off of the warp's ring: one TMA box, issued
+// by lane 0 (which re-derives the few parameters it needs from shared memory instead of keeping them in registers).
+__device__ __forceinline__ void stage_row(const Walk& w, int idx, int slot, int slot_off, int warp_ch, int b_pix0, int Wf) {
     if ((threadIdx.x & 31) == 0) {
+        const StreamShared& sh = *w.sh;
         const unsigned bar = w.full0 + slot * 8;
-        mbar_expect_tx(bar, w.box_bytes);
-        tma_box_g2s(w.dst + slot * w.slot_bytes, w.map, w.ch, w.pix0 + w.sh->rows[idx] * w.Wf, bar);
+        const int first_px = sh.first_px;
+        mbar_expect_tx(bar, (unsigned)(w.slot_bytes - first_px * kPixBytes));
+        tma_box_g2s(smem_u32(w.ring) + slot_off + first_px * kPixBytes, w.map, warp_ch, b_pix0 + sh.cmin + sh.rows[idx] * Wf, bar);
     }
 }
 
 // x-interpolate the next staged feature row (row k of the walk) at the 14 sample positions, then re-arm its slot.
-__device__ __forceinline__ void load_row(Walk& w, u64 (&X)[kS]) {
+// aoff[i] = byte offset of sample i's left pixel in a slot, wx[i] = its x_lerp: both live in registers for the whole RoI.
+__device__ __forceinline__ void load_row(Walk& w, u64 (&X)[kS], const int (&aoff)[kS], const float (&wx)[kS], int warp_ch,
+                                         int b_pix0, int Wf) {
     mbar_wait(w.full0 + w.slot * 8, w.phase);
-    const unsigned char* base = w.ring + w.slot * w.slot_bytes;
 #pragma unroll
     for (int i = 0; i < kS; ++i) {
-        const int4 e = w.sh->xt[i];
-        const u64 l = *reinterpret_cast<const u64*>(base + e.x);
-#ifdef FRCNN_EXP_NO_R
-        const u64 r = l ^ 0x0000000100000001ull;
-#else
-        const u64 r = *reinterpret_cast<const u64*>(base + e.x + kPixBytes);  // the right neighbour is the next pixel
-#endif
-        X[i] = lerp2(l, r, pack2(__int_as_float(e.z), __int_as_float(e.w)), w.one);
+        // aoff[i] is a complete shared-memory address for slot 0; the slot offset is warp-uniform, so the address is one
+        // register + one uniform register + an immediate (the right neighbour is the next pixel)
+        u64 l, r;
+        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(l) : "r"(aoff[i] + w.slot_off));
+        asm volatile("ld.shared.b64 %0, [%1+256];" : "=l"(r) : "r"(aoff[i] + w.slot_off));
+        X[i] = lerp2(l, r, pack2(wx[i], wx[i]), w.one);
     }
     __syncwarp();  // every lane has consumed its operands: the slot may be overwritten
-    if (w.k + w.depth < w.n_rows) stage_row(w, w.k + w.depth, w.slot);
+    if (w.k + w.depth < w.n_rows) stage_row(w, w.k + w.depth, w.slot, w.slot_off, warp_ch, b_pix0, Wf);
     ++w.k;
+    w.slot_off += w.slot_bytes;
     if (++w.slot == w.depth) {
         w.slot = 0;
+        w.slot_off = 0;
         w.phase ^= 1u;
     }
 }
@@ -219,9 +219,12 @@ __device__ __forceinline__ void crop_row(const u64 (&T)[kS], const u64 (&Bm)[kS]
     }
 }
 
+// kC = number of channels when known at compile time (1024: the reference's backbone; store offsets become immediates), 0 = any
+template <int kC>
 __global__ void __launch_bounds__(kThreads, 2)
-    roi_pool_fwd_stream_kernel(const __grid_constant__ TensorMaps maps, const float* __restrict__ feat, int Hf, int Wf, int C,
+    roi_pool_fwd_stream_kernel(const __grid_constant__ TensorMaps maps, const float* __restrict__ feat, int Hf, int Wf, int C_,
                                const float4* __restrict__ rois, int R, int nchunk, float* __restrict__ out) {
+    const int C = kC ? kC : C_;
     extern __shared__ __align__(128) unsigned char smem[];
     StreamShared& sh = *reinterpret_cast<StreamShared*>(smem);
     unsigned char* ring = smem + (sizeof(StreamShared) + 127) / 128 * 128;
@@ -276,13 +279,19 @@ __global__ void __launch_bounds__(kThreads, 2)
         } else if (shift) {
             sh.rows[off] = min(c + 1, last);
         }
-        if (lane < kS) {
-            sh.pos[lane] = v ? off + (load2 ? 2 : shift ? 1 : 0) - 1 : ((mv & lt) ? kPosAfter : kPosBefore);
-            sh.ylerp[lane] = ys.lerp;
-        }
+        // bit position of crop row sy = loads up to and including its bottom row + crop rows inside the map before it
+        const int bitpos = off + (load2 ? 2 : shift ? 1 : 0) + __popc(mv & lt);
+        const unsigned prog_lo = __reduce_or_sync(all, (v && bitpos < 32) ? (1u << bitpos) : 0u);
+        const unsigned prog_hi = __reduce_or_sync(all, (v && bitpos >= 32) ? (1u << (bitpos - 32)) : 0u);
+        const int n_before = __popc(__ballot_sync(all, lane < kS && !v && !(mv & lt)));
+        if (lane < kS) sh.ylerp[lane] = ys.lerp;
         if (lane == 0) {
             const int px = W + first_px;
             sh.n_rows = __popc(m1) + __popc(m2);
+            sh.prog_lo = prog_lo;
+            sh.prog_hi = prog_hi;
+            sh.n_before = n_before;
+            sh.n_after = kS - n_before - __popc(mv);
             sh.box = box;
             sh.cmin = sp.cmin;
             sh.first_px = first_px;
@@ -325,31 +334,40 @@ __global__ void __launch_bounds__(kThreads, 2)
         return;
     }
 
+    const unsigned all = 0xffffffffu;
     Walk w;
     w.sh = &sh;
     w.full0 = full_base + warp * (kMaxDepth * 8);
-    w.n_rows = sh.n_rows;
-    w.depth = sh.depth;
-    w.slot_bytes = sh.slot_bytes;
+    // (reduce_or of a warp-uniform value = the value, in a uniform register: loop control and slot offsets stay uniform)
+    w.n_rows = __reduce_or_sync(all, sh.n_rows);
+    w.depth = __reduce_or_sync(all, sh.depth);
+    w.slot_bytes = __reduce_or_sync(all, sh.slot_bytes);
     w.map = &maps.box[sh.box];
-    w.box_bytes = (unsigned)((sh.slot_bytes / kPixBytes - sh.first_px) * kPixBytes);
-    w.ch = ch0 + warp * kWarpCh;
-    w.pix0 = b * Hf * Wf + sh.cmin;
-    w.Wf = Wf;
-    w.dst = smem_u32(ring) + warp * kWarpRingBytes + sh.first_px * kPixBytes;
     w.ring = ring + warp * kWarpRingBytes + lane * 8;
     w.k = 0;
     w.slot = 0;
+    w.slot_off = 0;
     w.phase = 0;
     {
         const float onef = kOne;
         w.one = pack2(onef, onef);
     }
+    const int warp_ch = ch0 + warp * kWarpCh, b_pix0 = b * Hf * Wf;
     if (w.n_rows > 0) {
-        for (int s = 0; s < w.depth && s < w.n_rows; ++s) stage_row(w, s, s);
+        for (int s = 0; s < w.depth && s < w.n_rows; ++s) stage_row(w, s, s, s * w.slot_bytes, warp_ch, b_pix0, Wf);
         if (sh.first_px)  // the zero pixel of every slot (each lane later reads only what it wrote itself)
             for (int s = 0; s < w.depth; ++s) *reinterpret_cast<u64*>(const_cast<unsigned char*>(w.ring) + s * w.slot_bytes) = 0ull;
     }
+    int aoff[kS];
+    float wx[kS];
+#pragma unroll
+    for (int i = 0; i < kS; ++i) {
+        const int4 e = sh.xt[i];
+        aoff[i] = e.x + (int)smem_u32(w.ring);
+        wx[i] = __int_as_float(e.z);
+    }
+    u64 prog = ((u64)__reduce_or_sync(all, sh.prog_hi) << 32) | __reduce_or_sync(all, sh.prog_lo);
+    const int n_before = sh.n_before, n_after = sh.n_after;
 
     u64 X0[kS], X1[kS];
 #pragma unroll
@@ -358,42 +376,47 @@ __global__ void __launch_bounds__(kThreads, 2)
     float2* optr = reinterpret_cast<float2*>(out + ((size_t)b * R + r) * (kP * kP) * C + ch0) + tid;
     const int bin_stride = C / 2;  // float2 per bin
     int sy = 0;
-    int next_pos = sh.pos[0];
     // One finished crop row: fold it into the bin maxima; after the second row of a bin-row store the 7 bins.
     auto emit = [&](const u64 (&T)[kS], const u64 (&Bm)[kS], bool outside) {
-        const float yl = sh.ylerp[sy];
         if (!(sy & 1)) {
             if (outside) {  // crop row outside the map: extrapolation value 0 takes part in the max
 #pragma unroll
                 for (int j = 0; j < kP; ++j) M[j] = make_float2(0.0f, 0.0f);
             } else {
-                crop_row<true>(T, Bm, yl, w.one, M);
+                crop_row<true>(T, Bm, sh.ylerp[sy], w.one, M);
             }
         } else {
             if (outside) {
 #pragma unroll
                 for (int j = 0; j < kP; ++j) M[j] = make_float2(fmaxf(M[j].x, 0.0f), fmaxf(M[j].y, 0.0f));
             } else {
-                crop_row<false>(T, Bm, yl, w.one, M);
+                crop_row<false>(T, Bm, sh.ylerp[sy], w.one, M);
             }
 #pragma unroll
             for (int j = 0; j < kP; ++j) __stcs(optr + j * bin_stride, M[j]);
             optr += kP * bin_stride;
         }
         ++sy;
-        next_pos = sy < kS ? sh.pos[sy] : 1000;
     };
-    while (next_pos == kPosBefore) emit(X0, X1, true);
+    for (int i = 0; i < n_before; ++i) emit(X0, X1, true);
 #pragma unroll 1
     for (int k = 0; k < w.n_rows; k += 2) {
-        load_row(w, X0);  // even position: the new bottom row lands in set 0, set 1 holds the top row
-        while (next_pos == k) emit(X1, X0, false);
+        load_row(w, X0, aoff, wx, warp_ch, b_pix0, Wf);  // even position: the new bottom row lands in set 0, set 1 holds the top row
+        prog >>= 1;
+        while (prog & 1ull) {
+            emit(X1, X0, false);
+            prog >>= 1;
+        }
         if (k + 1 < w.n_rows) {
-            load_row(w, X1);
-            while (next_pos == k + 1) emit(X0, X1, false);
+            load_row(w, X1, aoff, wx, warp_ch, b_pix0, Wf);
+            prog >>= 1;
+            while (prog & 1ull) {
+                emit(X0, X1, false);
+                prog >>= 1;
+            }
         }
     }
-    while (sy < kS) emit(X0, X1, true);
+    for (int i = 0; i < n_after; ++i) emit(X0, X1, true);
 }
 
 // Host side: the eight tensor maps of a feature tensor, cached by (pointer, shape).
@@ -457,7 +480,8 @@ int launch_roi_pool_fwd_stream(const float* feat, int B, int Hf, int Wf, int C, 
     int dev = 0;
     FRCNN_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        FRCNN_CUDA(cudaFuncSetAttribute(roi_pool_fwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FRCNN_CUDA(cudaFuncSetAttribute(roi_pool_fwd_stream_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FRCNN_CUDA(cudaFuncSetAttribute(roi_pool_fwd_stream_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     const int nchunk = C / kChunk;
@@ -467,7 +491,10 @@ int launch_roi_pool_fwd_stream(const float* feat, int B, int Hf, int Wf, int C, 
     const int rc = get_tensor_maps(feat, (long long)B * Hf * Wf, C, dev, &maps);
     if (rc) return rc;
     const dim3 grid(R * nchunk, B);
-    roi_pool_fwd_stream_kernel<<<grid, kThreads, smem, st>>>(*maps, feat, Hf, Wf, C, (const float4*)rois, R, nchunk, out);
+    if (C == 1024)
+        roi_pool_fwd_stream_kernel<1024><<<grid, kThreads, smem, st>>>(*maps, feat, Hf, Wf, C, (const float4*)rois, R, nchunk, out);
+    else
+        roi_pool_fwd_stream_kernel<0><<<grid, kThreads, smem, st>>>(*maps, feat, Hf, Wf, C, (const float4*)rois, R, nchunk, out);
     FRCNN_LAUNCH_CHECK("roi_pool_fwd_stream_kernel");
     return 0;
 }

@@ -326,7 +326,7 @@ def run_b200_arm(args, w, syn):
         "overlap": "proposals of step i+1 (stream A) overlap RoI pooling of step i (stream B); double-buffered rois",
         "config": config_dict(w, args, {"l2": f"inputs rotate over {n_sets} sets ({n_sets * set_bytes / 1e6:.0f} MB > 126 MB L2); "
                                               f"{4 * B * w.max_total_size * 49 * w.channels / 1e6:.0f} MB pooled output per step"}),
-        "roofline": {"bound": "hbm", "kernel": "roi_pool_fwd_k2_kernel<2,128>", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "roi_pool_fwd_stream_kernel<1024>", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg["roi_pool_fwd"], "kernel_ms": pool_ms,
                      "frac_of_nominal_8TBps": achieved / 8000.0, "share_of_step": pool_ms / (ms_total / args.steps)},

@@ -397,7 +397,9 @@ static inline samp_t crop_coord(float c1, float c2, int extent, int S, int i) {
         in = 0.5f * (c1 + c2);
         in = in * (float)(extent - 1);
     }
-    if (in < 0.0f || in > (float)(extent - 1)) {
+    /* TF tests `in < 0 || in > extent - 1`; a NaN coordinate passes that test and then indexes out of bounds
+     * (undefined behaviour in the reference).  Defined choice here and in the CUDA path: NaN -> not sampled. */
+    if (!(in >= 0.0f && in <= (float)(extent - 1))) {
         r.valid = 0;
         r.lo = r.hi = 0;
         r.lerp = 0.0f;

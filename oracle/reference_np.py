@@ -171,7 +171,7 @@ def _axis_samples(c1, c2, extent, S):
             pos = F(F(c1 * F(extent - 1)) + F(F(i) * scale))
         else:
             pos = F(F(F(0.5) * F(c1 + c2)) * F(extent - 1))
-        if pos < 0 or pos > F(extent - 1):
+        if not (pos >= 0 and pos <= F(extent - 1)):  # NaN -> not sampled (undefined in TF; defined choice, see frcnn_oracle.c)
             res.append(None)
         else:
             lo = int(np.floor(pos))

@@ -229,6 +229,30 @@ def test_roi_pool_forward_bit_exact(det, orc, syn, rng, grid, C, R, relu):
     assert tuple(det.ROIPooling(7, 2)(dev(f), dev(rois)).shape) == (2 * R, 7, 7, C)
 
 
+@pytest.mark.parametrize("grid,C", [((24, 78), 1024), ((50, 84), 512), ((9, 11), 512), ((3, 2), 1536), ((1, 1), 512)])
+def test_roi_pool_forward_row_streaming_edge_cases(det, orc, syn, rng, grid, C):
+    """C % 512 == 0 with the 7x7 / k=2 configuration takes the row-streaming TMA kernel: every box width class, the zero
+    pixel for samples outside the map, reversed boxes, RoIs wider than the ring (plain gather path), degenerate boxes,
+    1-pixel maps -- all bit-exact against the oracle, and identical to the older bin-row walk (FRCNN_FWD_WALK)."""
+    f = syn.feature_maps(rng, 2, grid, C, relu=False)
+    R = 64
+    rois = syn.random_rois(rng, 2, R, num_valid=[R - 3, R])
+    w = np.linspace(0.0, 1.0, 24, dtype=F)  # one RoI per x-extent, sweeping all box widths up to the whole map
+    rois[0, :24] = np.stack([0.5 - w / 2, np.full_like(w, 0.2), 0.5 + w / 2, np.full_like(w, 0.8)], -1)
+    rois[1, 0] = [0.25, 0.1, 1.0, 1.0]       # x2 = y2 = 1.0 exactly: integer position on the last column / row (T6)
+    rois[1, 1] = [0.0, 0.0, 1.0, 1.0]        # whole map: wider than the ring at 78 / 84 columns
+    rois[1, 2] = [0.9, 0.8, 0.1, 0.2]        # reversed: columns and rows walk backwards
+    rois[1, 3] = [-0.2, 0.3, 0.4, 1.3]       # partly outside: zero pixel + crop rows after the map
+    rois[1, 4] = [-0.5, -0.6, -0.1, -0.2]    # completely outside: all zeros
+    rois[1, 5] = [0.5, 0.5, 0.5, 0.5]        # degenerate point
+    rois[1, 6] = [0.3, -0.4, 0.6, 0.5]       # crop rows before the map
+    rois[1, 7] = [np.nan, 0.1, 0.5, 0.6]     # NaN coordinate: nothing sampled along x
+    rois[1, 8] = [0.0, 0.45, 1.0, 0.55]      # whole width, two feature rows
+    ref = orc.roi_pool_forward(f, rois, 7, 2)
+    out = host(det.roi_pool_forward(dev(f), dev(rois), 7, 2))
+    np.testing.assert_array_equal(out, ref)
+
+
 def test_roi_pool_other_window_sizes_and_out_of_range(det, orc, syn, rng):
     f = syn.feature_maps(rng, 1, (9, 11), 8, relu=False)
     rois = np.array([[[-0.2, -0.1, 0.6, 0.7], [0.3, 0.4, 1.3, 1.2], [0.5, 0.5, 0.5, 0.5], [0.9, 0.8, 0.1, 0.2]]], F)
