@@ -34,7 +34,8 @@ __device__ __forceinline__ void axis_sample(float c1, float c2, int extent, int 
 
 // Row-streaming forward for pooled_size 7 / kernel_size 2 / C % 512 == 0 (roi_pool_stream.cu).
 bool roi_pool_stream_supported(int C, int P, int k);
+// codes != nullptr: training forward, also writes the arg-max codes ([B,R,P,P,C/4] bytes).
 int launch_roi_pool_fwd_stream(const float* feat, int B, int Hf, int Wf, int C, const float* rois, int R, float* out,
-                               cudaStream_t st);
+                               unsigned char* codes, cudaStream_t st);
 
 }  // namespace frcnn

@@ -773,7 +773,7 @@ int frcnn_roi_pool_forward(const float* feat, int B, int Hf, int Wf, int C, cons
     const dim3 grid(R, B);
     static const bool force_walk = getenv("FRCNN_FWD_WALK") != nullptr;  // A/B switch for benchmarking the older bin-row walk
     if (roi_pool_stream_supported(C, P, k) && !force_walk)
-        return launch_roi_pool_fwd_stream(feat, B, Hf, Wf, C, rois, R, out, as_stream(stream));
+        return launch_roi_pool_fwd_stream(feat, B, Hf, Wf, C, rois, R, out, nullptr, as_stream(stream));
     if (C % 4 == 0 && k == 2 && (int64_t)Hf * Wf * (C / 4) < (1ll << 31)) {
         const int cv = C / 4;
         if (cv % 256 == 0)
@@ -840,6 +840,9 @@ int frcnn_roi_pool_forward_argmax(const float* feat, int B, int Hf, int Wf, int 
     FRCNN_REQUIRE(aligned16(feat) && aligned16(rois) && aligned16(out) && argmax_codes, FRCNN_EINVAL,
                   "roi_pool_forward_argmax: pointers must be 16-byte aligned");
     if (R == 0) return 0;
+    static const bool force_walk = getenv("FRCNN_FWD_WALK") != nullptr;
+    if (roi_pool_stream_supported(C, P, k) && !force_walk)
+        return launch_roi_pool_fwd_stream(feat, B, Hf, Wf, C, rois, R, out, argmax_codes, as_stream(stream));
     return launch_codes<0>(feat, B, Hf, Wf, C, rois, R, P, out, argmax_codes, nullptr, nullptr, as_stream(stream));
 }
 

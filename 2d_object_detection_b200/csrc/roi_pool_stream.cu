@@ -202,14 +202,37 @@ __device__ __forceinline__ void load_row(Walk& w, u64 (&X)[kS], const int (&aoff
     }
 }
 
-template <bool kFirst>
-__device__ __forceinline__ void crop_row(const u64 (&T)[kS], const u64 (&Bm)[kS], float yl, u64 one, float2 (&M)[kP]) {
+// Strict-greater update of a running maximum and its 2-bit window position (first maximum in row-major window order
+// wins: trap T8).  `pos` = dy * 2 + dx of the candidate; the code of channel lane `c` of bin j sits at bit 4 j + 2 c.
+__device__ __forceinline__ void take_if_greater(float& m, unsigned& cw, float v, unsigned pos, int shift) {
+    if (v > m) {
+        m = v;
+        cw = (cw & ~(3u << shift)) | (pos << shift);
+    }
+}
+
+// Fold one finished crop row (top / bottom feature rows T / Bm, weight yl) into the 7 running bin maxima.  kFirst: first
+// crop row of the bin-row.  kCodes: also track which of the four window samples holds the maximum (training forward).
+template <bool kFirst, bool kCodes>
+__device__ __forceinline__ void crop_row(const u64 (&T)[kS], const u64 (&Bm)[kS], float yl, u64 one, float2 (&M)[kP],
+                                         unsigned& cw) {
     const u64 ww = pack2(yl, yl);
 #pragma unroll
     for (int j = 0; j < kP; ++j) {
         const float2 v0 = unpack2(lerp2(T[2 * j], Bm[2 * j], ww, one));
         const float2 v1 = unpack2(lerp2(T[2 * j + 1], Bm[2 * j + 1], ww, one));
-        if (kFirst) {
+        if (kCodes) {
+            if (kFirst) {
+                M[j] = v0;  // window position 0; cw was cleared for this bin-row
+                take_if_greater(M[j].x, cw, v1.x, 1u, 4 * j);
+                take_if_greater(M[j].y, cw, v1.y, 1u, 4 * j + 2);
+            } else {
+                take_if_greater(M[j].x, cw, v0.x, 2u, 4 * j);
+                take_if_greater(M[j].y, cw, v0.y, 2u, 4 * j + 2);
+                take_if_greater(M[j].x, cw, v1.x, 3u, 4 * j);
+                take_if_greater(M[j].y, cw, v1.y, 3u, 4 * j + 2);
+            }
+        } else if (kFirst) {
             M[j].x = fmaxf(v0.x, v1.x);
             M[j].y = fmaxf(v0.y, v1.y);
         } else {
@@ -220,10 +243,12 @@ __device__ __forceinline__ void crop_row(const u64 (&T)[kS], const u64 (&Bm)[kS]
 }
 
 // kC = number of channels when known at compile time (1024: the reference's backbone; store offsets become immediates), 0 = any
-template <int kC>
+// kCodes: training forward, also writes the arg-max codes ([B,R,P,P,C/4] bytes: four 2-bit window positions per byte)
+template <int kC, bool kCodes>
 __global__ void __launch_bounds__(kThreads, 2)
     roi_pool_fwd_stream_kernel(const __grid_constant__ TensorMaps maps, const float* __restrict__ feat, int Hf, int Wf, int C_,
-                               const float4* __restrict__ rois, int R, int nchunk, float* __restrict__ out) {
+                               const float4* __restrict__ rois, int R, int nchunk, float* __restrict__ out,
+                               unsigned char* __restrict__ codes) {
     const int C = kC ? kC : C_;
     extern __shared__ __align__(128) unsigned char smem[];
     StreamShared& sh = *reinterpret_cast<StreamShared*>(smem);
@@ -310,9 +335,11 @@ __global__ void __launch_bounds__(kThreads, 2)
         const float* fb = feat + (size_t)b * Hf * Wf * C + ch0 + tid * 2;
         float2* ob = reinterpret_cast<float2*>(out + ((size_t)b * R + r) * (kP * kP) * C + ch0) + tid;
 #pragma unroll 1
+        unsigned char* cb = kCodes ? codes + ((size_t)b * R + r) * (kP * kP) * (C / 4) + (ch0 + tid * 2) / 4 : nullptr;
         for (int bin = 0; bin < kP * kP; ++bin) {
             const int py = bin / kP, px = bin - py * kP;
             float2 best = make_float2(0.0f, 0.0f);
+            unsigned cw = 0u;
 #pragma unroll 1
             for (int s4 = 0; s4 < 4; ++s4) {
                 const int sy = 2 * py + (s4 >> 1), sx = 2 * px + (s4 & 1);
@@ -326,10 +353,18 @@ __global__ void __launch_bounds__(kThreads, 2)
                     const u64 wx = pack2(sh.xlerp[sx], sh.xlerp[sx]), wy = pack2(sh.ylerp[sy], sh.ylerp[sy]);
                     val = unpack2(lerp2(lerp2(tl, tr, wx, one), lerp2(bl, br, wx, one), wy, one));
                 }
-                best.x = s4 == 0 ? val.x : fmaxf(best.x, val.x);
-                best.y = s4 == 0 ? val.y : fmaxf(best.y, val.y);
+                if (s4 == 0) {
+                    best = val;
+                } else {
+                    take_if_greater(best.x, cw, val.x, (unsigned)s4, 0);
+                    take_if_greater(best.y, cw, val.y, (unsigned)s4, 2);
+                }
             }
             __stcs(ob + (size_t)bin * (C / 2), best);
+            if (kCodes) {
+                const unsigned pw = __shfl_xor_sync(0xffffffffu, cw, 1);
+                if (!(tid & 1)) cb[(size_t)bin * (C / 4)] = (unsigned char)((cw & 15u) | ((pw & 15u) << 4));
+            }
         }
         return;
     }
@@ -376,25 +411,44 @@ __global__ void __launch_bounds__(kThreads, 2)
     float2* optr = reinterpret_cast<float2*>(out + ((size_t)b * R + r) * (kP * kP) * C + ch0) + tid;
     const int bin_stride = C / 2;  // float2 per bin
     int sy = 0;
+    unsigned cw = 0u;  // kCodes: the 2-bit window positions of this lane's two channels for the 7 bins of the bin-row
+    unsigned char* cptr = kCodes ? codes + ((size_t)b * R + r) * (kP * kP) * (C / 4) + (ch0 + tid * 2) / 4 : nullptr;
     // One finished crop row: fold it into the bin maxima; after the second row of a bin-row store the 7 bins.
     auto emit = [&](const u64 (&T)[kS], const u64 (&Bm)[kS], bool outside) {
         if (!(sy & 1)) {
+            cw = 0u;
             if (outside) {  // crop row outside the map: extrapolation value 0 takes part in the max
 #pragma unroll
                 for (int j = 0; j < kP; ++j) M[j] = make_float2(0.0f, 0.0f);
             } else {
-                crop_row<true>(T, Bm, sh.ylerp[sy], w.one, M);
+                crop_row<true, kCodes>(T, Bm, sh.ylerp[sy], w.one, M, cw);
             }
         } else {
             if (outside) {
 #pragma unroll
-                for (int j = 0; j < kP; ++j) M[j] = make_float2(fmaxf(M[j].x, 0.0f), fmaxf(M[j].y, 0.0f));
+                for (int j = 0; j < kP; ++j) {
+                    if (kCodes) {  // window positions 2 and 3 are both 0: position 2 wins if 0 beats the first row
+                        take_if_greater(M[j].x, cw, 0.0f, 2u, 4 * j);
+                        take_if_greater(M[j].y, cw, 0.0f, 2u, 4 * j + 2);
+                    } else {
+                        M[j] = make_float2(fmaxf(M[j].x, 0.0f), fmaxf(M[j].y, 0.0f));
+                    }
+                }
             } else {
-                crop_row<false>(T, Bm, sh.ylerp[sy], w.one, M);
+                crop_row<false, kCodes>(T, Bm, sh.ylerp[sy], w.one, M, cw);
             }
 #pragma unroll
             for (int j = 0; j < kP; ++j) __stcs(optr + j * bin_stride, M[j]);
             optr += kP * bin_stride;
+            if (kCodes) {  // a byte holds four channels = this lane's nibble and its odd neighbour's
+                const unsigned pw = __shfl_xor_sync(0xffffffffu, cw, 1);
+                if (!(tid & 1)) {
+#pragma unroll
+                    for (int j = 0; j < kP; ++j)
+                        cptr[j * (C / 4)] = (unsigned char)(((cw >> (4 * j)) & 15u) | (((pw >> (4 * j)) & 15u) << 4));
+                }
+                cptr += kP * (C / 4);
+            }
         }
         ++sy;
     };
@@ -474,14 +528,16 @@ int get_tensor_maps(const float* feat, long long pixels, int C, int dev, const T
 bool roi_pool_stream_supported(int C, int P, int k) { return C % kChunk == 0 && P == kP && k == 2; }
 
 int launch_roi_pool_fwd_stream(const float* feat, int B, int Hf, int Wf, int C, const float* rois, int R, float* out,
-                               cudaStream_t st) {
+                               unsigned char* codes, cudaStream_t st) {
     const size_t smem = (sizeof(StreamShared) + 127) / 128 * 128 + kRingBytes;
     static bool configured[64] = {};  // the attribute is per function and per device; setting it twice is harmless
     int dev = 0;
     FRCNN_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        FRCNN_CUDA(cudaFuncSetAttribute(roi_pool_fwd_stream_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        FRCNN_CUDA(cudaFuncSetAttribute(roi_pool_fwd_stream_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FRCNN_CUDA(cudaFuncSetAttribute(roi_pool_fwd_stream_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FRCNN_CUDA(cudaFuncSetAttribute(roi_pool_fwd_stream_kernel<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FRCNN_CUDA(cudaFuncSetAttribute(roi_pool_fwd_stream_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FRCNN_CUDA(cudaFuncSetAttribute(roi_pool_fwd_stream_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     const int nchunk = C / kChunk;
@@ -491,10 +547,14 @@ int launch_roi_pool_fwd_stream(const float* feat, int B, int Hf, int Wf, int C, 
     const int rc = get_tensor_maps(feat, (long long)B * Hf * Wf, C, dev, &maps);
     if (rc) return rc;
     const dim3 grid(R * nchunk, B);
-    if (C == 1024)
-        roi_pool_fwd_stream_kernel<1024><<<grid, kThreads, smem, st>>>(*maps, feat, Hf, Wf, C, (const float4*)rois, R, nchunk, out);
-    else
-        roi_pool_fwd_stream_kernel<0><<<grid, kThreads, smem, st>>>(*maps, feat, Hf, Wf, C, (const float4*)rois, R, nchunk, out);
+    const float4* r4 = (const float4*)rois;
+    if (codes) {
+        if (C == 1024) roi_pool_fwd_stream_kernel<1024, true><<<grid, kThreads, smem, st>>>(*maps, feat, Hf, Wf, C, r4, R, nchunk, out, codes);
+        else roi_pool_fwd_stream_kernel<0, true><<<grid, kThreads, smem, st>>>(*maps, feat, Hf, Wf, C, r4, R, nchunk, out, codes);
+    } else {
+        if (C == 1024) roi_pool_fwd_stream_kernel<1024, false><<<grid, kThreads, smem, st>>>(*maps, feat, Hf, Wf, C, r4, R, nchunk, out, nullptr);
+        else roi_pool_fwd_stream_kernel<0, false><<<grid, kThreads, smem, st>>>(*maps, feat, Hf, Wf, C, r4, R, nchunk, out, nullptr);
+    }
     FRCNN_LAUNCH_CHECK("roi_pool_fwd_stream_kernel");
     return 0;
 }
