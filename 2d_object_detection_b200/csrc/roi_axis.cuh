@@ -38,4 +38,8 @@ bool roi_pool_stream_supported(int C, int P, int k);
 int launch_roi_pool_fwd_stream(const float* feat, int B, int Hf, int Wf, int C, const float* rois, int R, float* out,
                                unsigned char* codes, cudaStream_t st);
 
+// Backward from the saved arg-max codes on the same walk (TMA reduce-add rows); dfeat must already be zeroed.
+int launch_roi_pool_bwd_stream(int B, int Hf, int Wf, int C, const float* rois, int R, const float* dy,
+                               const unsigned char* codes, float* dfeat, cudaStream_t st);
+
 }  // namespace frcnn

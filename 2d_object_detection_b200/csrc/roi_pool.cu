@@ -855,6 +855,9 @@ int frcnn_roi_pool_backward_argmax(int B, int Hf, int Wf, int C, const float* ro
                   "roi_pool_backward_argmax: pointers must be 16-byte aligned");
     FRCNN_CUDA(cudaMemsetAsync(dfeat, 0, sizeof(float) * (size_t)B * Hf * Wf * C, as_stream(stream)));
     if (R == 0) return 0;
+    static const bool force_walk = getenv("FRCNN_BWD_WALK") != nullptr;  // A/B switch: the older bin-row walk
+    if (roi_pool_stream_supported(C, P, k) && !force_walk)
+        return launch_roi_pool_bwd_stream(B, Hf, Wf, C, rois, R, dy, argmax_codes, dfeat, as_stream(stream));
     return launch_codes<1>(nullptr, B, Hf, Wf, C, rois, R, P, nullptr, const_cast<unsigned char*>(argmax_codes), dy, dfeat,
                            as_stream(stream));
 }

@@ -473,10 +473,391 @@ __global__ void __launch_bounds__(kThreads, 2)
     for (int i = 0; i < n_after; ++i) emit(X0, X1, true);
 }
 
+
+// ================================================================================================
+// Backward from saved arg-max codes: the mirror image of the walk above (models/faster_rcnn.py:73,103 differentiates
+// ROIPooling; MaxPoolGrad routes dY to the arg-max sample, CropAndResizeGradImage scatters the four bilinear shares).
+//   * dY and the codes of one bin-row (7 bins x 64 channels = 1792 B, 7 x 16 code bytes) arrive by TMA in a 3-slot ring.
+//   * The two register row sets now ACCUMULATE: a crop row adds (1 - yl) g to the set of its top feature row and yl g to
+//     the set of its bottom row, at its 14 x-sample positions (g = dY of the bin if this sample is the bin's arg-max
+//     for the channel, else 0).
+//   * When the walk leaves a feature row its set is scattered along x -- sample i gives (1 - xl) G[i] to pixel lo and
+//     xl G[i] to pixel lo + 1 of a lane-private shared-memory row buffer (plain read-modify-write, no atomics) -- and
+//     ONE cp.reduce.async.bulk.tensor (TMA reduce-add, fp32) adds the buffer to dFeature: W pixels x 64 channels per
+//     instruction instead of W x 16 vector atomics.
+// The gradient has no reference summation order (TF: atomics on GPU, a sequential loop on CPU); the bar is 1e-5
+// relative, so contributions are fused multiply-adds and the y-sum is formed before the x-weights are applied.
+// RoIs that do not fit (x-samples more than 25 columns apart) take a plain atomic path.
+// ================================================================================================
+constexpr int kBwdRowPix = 30;                         // per-warp row-buffer ring, pixels
+constexpr int kBwdMaxBufs = 4;
+constexpr int kBwdDySlots = 3;
+constexpr int kBwdDyBytes = kP * kPixBytes;            // 7 bins x 64 channels x 4 B
+constexpr int kBwdCodeBytes = 128;                     // 7 bins x 16 code bytes, padded
+constexpr int kBwdWarpBytes = kBwdRowPix * kPixBytes + 2 * kPixBytes + kBwdDySlots * (kBwdDyBytes + kBwdCodeBytes);
+constexpr int kBwdNumBoxes = 7;                        // box widths 6 .. 26 (box_width(0..6))
+
+struct BwdMaps {
+    CUtensorMap dfeat[kBwdNumBoxes];  // [B*Hf*Wf, C] fp32, box 64 x W: reduce-add target
+    CUtensorMap dy;                   // [B*R*49, C] fp32, box 64 x 7
+    CUtensorMap codes;                // [B*R*49, C/4] u8, box 16 x 7
+};
+
+struct BwdShared {
+    int4 xt[kS];          // per crop column: {left pixel byte offset in a row buffer, 0, x_lerp bits, x_lerp bits}
+    float ylerp[kS];
+    int rows[2 * kS];
+    int n_rows, box, cmin, W, nbufs, slow;
+    unsigned prog_lo, prog_hi, xokmask;  // xokmask bit i: crop column i lies inside the map
+    int n_before, n_after;
+    int xlo[kS], xhi[kS], xok[kS], ylo[kS], yhi[kS], yok[kS];  // plain sample tables for the slow path
+    float xlerp[kS];
+    unsigned long long dfull[kWarps][kBwdDySlots];
+};
+
+__device__ __forceinline__ void tma_reduce_add_s2g(const CUtensorMap* map, int c0, int c1, unsigned src) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map),
+                 "r"(c0), "r"(c1), "r"(src)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read(int pending) {  // wait until at most `pending` groups still read smem
+    switch (pending) {
+        case 0: asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); break;
+        default: asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory"); break;
+    }
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ void sts64(unsigned addr, u64 v) { asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory"); }
+
+struct BwdWalk {
+    BwdShared* sh;
+    const BwdMaps* maps;
+    unsigned warp_smem;   // shared address of this warp's region: row buffers | 2 scratch pixels | dY slots | code slots
+    unsigned lane_smem;   // warp_smem + this lane's channel offset
+    unsigned dfull0;      // shared address of this warp's dfull[0]
+    int warp_ch, W, nbufs, buf, buf_off, issued;
+    unsigned xok;         // bit i: crop column i lies inside the map
+};
+
+// One crop row inside the map: route dY of its 7 bins to the samples that won the max, weight by (1 - yl) / yl.
+template <bool kSecond>
+__device__ __forceinline__ void bwd_crop_row(u64 (&T)[kS], u64 (&Bm)[kS], float yl, unsigned dy_addr, unsigned cw) {
+    const float wt = fsub(1.0f, yl);
+    const u64 wt2 = pack2(wt, wt), wb2 = pack2(yl, yl);
+#pragma unroll
+    for (int j = 0; j < kP; ++j) {
+        u64 dyv;
+        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(dyv) : "r"(dy_addr + j * kPixBytes));
+        const float2 d = unpack2(dyv);
+        const unsigned cx = (cw >> (4 * j)) & 3u, cy = (cw >> (4 * j + 2)) & 3u;
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+            const unsigned pos = (kSecond ? 2u : 0u) + (unsigned)dx;
+            const u64 g = pack2(cx == pos ? d.x : 0.0f, cy == pos ? d.y : 0.0f);
+            T[2 * j + dx] = fma2(g, wt2, T[2 * j + dx]);
+            Bm[2 * j + dx] = fma2(g, wb2, Bm[2 * j + dx]);
+        }
+    }
+}
+
+__device__ __forceinline__ u64 lds64(unsigned addr) {
+    u64 v;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+// The walk has left feature row rows[kk]: scatter its accumulated set along x into a zeroed row buffer -- sample i adds
+// (1 - xl) G[i] to pixel lo and xl G[i] to pixel lo + 1; every lane owns its own two channels of the buffer, so these are
+// plain shared-memory read-modify-writes in program order -- and hand the buffer to the TMA engine, which adds it to
+// dFeature (one cp.reduce.async.bulk.tensor per feature row and warp).
+__device__ __forceinline__ void bwd_flush(BwdWalk& w, u64 (&G)[kS], const float (&wx)[kS], const int (&aoff)[kS], int kk,
+                                          int b_pix0, int Wf) {
+    const int lane = threadIdx.x & 31;
+    if (w.issued >= w.nbufs) {  // the buffer about to be reused must have been read by its reduce
+        if (lane == 0) bulk_wait_read(w.nbufs - 1);
+        __syncwarp();
+    }
+    unsigned buf = w.lane_smem + w.buf_off;
+    asm volatile("" : "+r"(buf));  // keep the address in a register (ptxas otherwise rebuilds it from %tid for every sample)
+#pragma unroll 2
+    for (int p = 0; p < w.W; ++p) sts64(buf + p * kPixBytes, 0ull);
+#pragma unroll
+    for (int i = 0; i < kS; ++i) {
+        if ((w.xok >> i) & 1u) {  // samples outside the map receive no gradient (uniform branch)
+            const float xl = wx[i];
+            const float xr = fsub(1.0f, xl);
+            const unsigned a = buf + aoff[i];
+            const u64 lo = lds64(a), hi = lds64(a + kPixBytes);
+            sts64(a, fma2(G[i], pack2(xr, xr), lo));
+            sts64(a + kPixBytes, fma2(G[i], pack2(xl, xl), hi));
+        }
+        G[i] = 0ull;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the TMA engine
+    __syncwarp();
+    if (lane == 0)
+        tma_reduce_add_s2g(&w.maps->dfeat[w.sh->box], w.warp_ch, b_pix0 + w.sh->cmin + w.sh->rows[kk] * Wf, w.warp_smem + w.buf_off);
+    ++w.issued;
+    w.buf_off += w.W * kPixBytes;
+    if (++w.buf == w.nbufs) {
+        w.buf = 0;
+        w.buf_off = 0;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+    roi_pool_bwd_stream_kernel(const __grid_constant__ BwdMaps maps, int Hf, int Wf, int C, const float4* __restrict__ rois, int R,
+                               int nchunk, const float* __restrict__ dy, const unsigned char* __restrict__ codes,
+                               float* __restrict__ dfeat) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    BwdShared& sh = *reinterpret_cast<BwdShared*>(smem);
+    unsigned char* region = smem + (sizeof(BwdShared) + 127) / 128 * 128;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r = blockIdx.x / nchunk, ch0 = (blockIdx.x % nchunk) * kChunk, b = blockIdx.y;
+    const unsigned dfull_base = smem_u32(&sh.dfull[0][0]);
+    const unsigned all = 0xffffffffu;
+
+    if (tid < 32) {
+        const float4 roi = rois[(size_t)b * R + r];
+        const Sample xs = sample_axis(roi.x, roi.z, Wf, lane);
+        const Sample ys = sample_axis(roi.y, roi.w, Hf, lane);
+        const Span sp = column_span(xs, lane);
+        int box = 0;
+#pragma unroll
+        for (int i = 0; i < kNumBoxes; ++i) box += (sp.need > box_width(i)) ? 1 : 0;
+        int W = 0;
+#pragma unroll
+        for (int i = 0; i < kNumBoxes; ++i) W = (box == i) ? box_width(i) : W;
+        const unsigned xokmask = __ballot_sync(all, lane < kS && xs.ok);
+        const bool slow = box >= kBwdNumBoxes;
+        if (lane < kS) {
+            const int lerp = xs.ok ? __float_as_int(xs.lerp) : 0;
+            sh.xt[lane] = make_int4(xs.ok ? (xs.lo - sp.cmin) * kPixBytes : 0, 0, lerp, lerp);
+            sh.xlo[lane] = xs.lo; sh.xhi[lane] = xs.hi; sh.xok[lane] = xs.ok; sh.xlerp[lane] = xs.lerp;
+            sh.ylo[lane] = ys.lo; sh.yhi[lane] = ys.hi; sh.yok[lane] = ys.ok; sh.ylerp[lane] = ys.lerp;
+        }
+        // the downward walk, exactly as in the forward kernel
+        const bool anyx = sp.need > 0;
+        const bool v = lane < kS && ys.ok && anyx;
+        const int c = ys.lo;
+        const int pv_i = __shfl_up_sync(all, (int)v, 1);
+        const bool pv = pv_i != 0 && lane > 0;
+        const int pc = __shfl_up_sync(all, c, 1);
+        const bool reuse = v && pv && c == pc;
+        const bool shift = v && pv && c == pc + 1;
+        const bool load2 = v && !reuse && !shift;
+        const unsigned lt = (1u << lane) - 1u;
+        const unsigned m1 = __ballot_sync(all, shift || load2), m2 = __ballot_sync(all, load2);
+        const int off = __popc(m1 & lt) + __popc(m2 & lt);
+        const unsigned mv = __ballot_sync(all, v);
+        const int last = Hf - 1;
+        if (load2) {
+            sh.rows[off] = c;
+            sh.rows[off + 1] = min(c + 1, last);
+        } else if (shift) {
+            sh.rows[off] = min(c + 1, last);
+        }
+        const int bitpos = off + (load2 ? 2 : shift ? 1 : 0) + __popc(mv & lt);
+        const unsigned prog_lo = __reduce_or_sync(all, (v && bitpos < 32) ? (1u << bitpos) : 0u);
+        const unsigned prog_hi = __reduce_or_sync(all, (v && bitpos >= 32) ? (1u << (bitpos - 32)) : 0u);
+        const int n_before = __popc(__ballot_sync(all, lane < kS && !v && !(mv & lt)));
+        if (lane == 0) {
+            sh.n_rows = __popc(m1) + __popc(m2);
+            sh.prog_lo = prog_lo;
+            sh.prog_hi = prog_hi;
+            sh.xokmask = xokmask;
+            sh.n_before = n_before;
+            sh.n_after = kS - n_before - __popc(mv);
+            sh.box = box;
+            sh.cmin = sp.cmin;
+            sh.W = W;
+            sh.nbufs = max(1, min(kBwdMaxBufs, kBwdRowPix / max(W, 1)));
+            sh.slow = slow ? 1 : 0;
+        }
+    } else if (tid < 32 + kWarps * kBwdDySlots) {
+        mbar_init(dfull_base + (tid - 32) * 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const size_t bin0 = ((size_t)b * R + r) * (kP * kP);
+    if (sh.slow) {  // rare: one atomic per bilinear share, TF's operation order
+        const float* gy = dy + bin0 * C + ch0 + tid * 2;
+        const unsigned char* cb = codes + bin0 * (C / 4) + (ch0 + tid * 2) / 4;
+        float* gb = dfeat + (size_t)b * Hf * Wf * C + ch0 + tid * 2;
+#pragma unroll 1
+        for (int bin = 0; bin < kP * kP; ++bin) {
+            const int py = bin / kP, px = bin - py * kP;
+            const float2 g2 = *reinterpret_cast<const float2*>(gy + (size_t)bin * C);
+            const unsigned nib = (cb[(size_t)bin * (C / 4)] >> ((tid & 1) * 4)) & 15u;
+#pragma unroll 1
+            for (int cidx = 0; cidx < 2; ++cidx) {
+                const unsigned pos = (nib >> (2 * cidx)) & 3u;
+                const int sy = 2 * py + (int)(pos >> 1), sx = 2 * px + (int)(pos & 1u);
+                if (!(sh.yok[sy] && sh.xok[sx])) continue;  // the extrapolation value won: no gradient
+                const float g = cidx ? g2.y : g2.x;
+                const float yl = sh.ylerp[sy], xl = sh.xlerp[sx];
+                const float dtop = fmul(fsub(1.0f, yl), g), dbot = fmul(yl, g);
+                float* top = gb + (size_t)sh.ylo[sy] * Wf * C + cidx;
+                float* bot = gb + (size_t)sh.yhi[sy] * Wf * C + cidx;
+                atomicAdd(top + (size_t)sh.xlo[sx] * C, fmul(fsub(1.0f, xl), dtop));
+                atomicAdd(top + (size_t)sh.xhi[sx] * C, fmul(xl, dtop));
+                atomicAdd(bot + (size_t)sh.xlo[sx] * C, fmul(fsub(1.0f, xl), dbot));
+                atomicAdd(bot + (size_t)sh.xhi[sx] * C, fmul(xl, dbot));
+            }
+        }
+        return;
+    }
+
+    BwdWalk w;
+    w.sh = &sh;
+    w.maps = &maps;
+    w.warp_smem = smem_u32(region) + warp * kBwdWarpBytes;
+    asm volatile("" : "+r"(w.warp_smem));
+    w.lane_smem = w.warp_smem + lane * 8;
+    asm volatile("" : "+r"(w.lane_smem));
+    w.dfull0 = dfull_base + warp * (kBwdDySlots * 8);
+    w.warp_ch = ch0 + warp * kWarpCh;
+    w.W = __reduce_or_sync(all, sh.W);
+    w.nbufs = __reduce_or_sync(all, sh.nbufs);
+    w.buf = 0;
+    w.buf_off = 0;
+    w.issued = 0;
+    w.xok = __reduce_or_sync(all, sh.xokmask);
+    const int n_rows = __reduce_or_sync(all, sh.n_rows);
+    const int b_pix0 = b * Hf * Wf;
+    const unsigned dy_slots = w.warp_smem + (kBwdRowPix + 2) * kPixBytes;
+    const unsigned code_slots = dy_slots + kBwdDySlots * kBwdDyBytes;
+    // stage dY + codes of bin-row `py` into slot py % 3 (lane 0)
+    auto stage_bin_row = [&](int py, int slot) {
+        if (lane == 0) {
+            const unsigned bar = w.dfull0 + slot * 8;
+            mbar_expect_tx(bar, kBwdDyBytes + kP * 16);
+            tma_box_g2s(dy_slots + slot * kBwdDyBytes, &maps.dy, w.warp_ch, (int)bin0 + py * kP, bar);
+            tma_box_g2s(code_slots + slot * kBwdCodeBytes, &maps.codes, w.warp_ch / 4, (int)bin0 + py * kP, bar);
+        }
+    };
+    for (int py = 0; py < kBwdDySlots; ++py) stage_bin_row(py, py);
+
+    float wx[kS];
+    int aoff[kS];
+#pragma unroll
+    for (int i = 0; i < kS; ++i) {
+        const int4 e = sh.xt[i];
+        aoff[i] = e.x;
+        wx[i] = __int_as_float(e.z);
+    }
+    u64 prog = ((u64)__reduce_or_sync(all, sh.prog_hi) << 32) | __reduce_or_sync(all, sh.prog_lo);
+    const int n_before = sh.n_before, n_after = sh.n_after;
+    u64 G0[kS], G1[kS];
+#pragma unroll
+    for (int i = 0; i < kS; ++i) G0[i] = G1[i] = 0ull;
+    int sy = 0, dslot = 0;
+    unsigned dphase = 0;
+    // One crop row: wait for its bin-row's dY, accumulate (unless it lies outside the map), release the slot after the
+    // second row of the bin-row and re-arm it with the bin-row three further down.
+    auto crop = [&](u64 (&T)[kS], u64 (&Bm)[kS], bool outside) {
+        mbar_wait(w.dfull0 + dslot * 8, dphase);
+        if (!outside) {
+            unsigned cw = 0u;
+#pragma unroll
+            for (int j = 0; j < kP; ++j) {
+                unsigned byte;
+                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(byte) : "r"(code_slots + dslot * kBwdCodeBytes + j * 16 + (lane >> 1)));
+                cw |= ((byte >> ((lane & 1) * 4)) & 15u) << (4 * j);
+            }
+            unsigned dy_addr = w.lane_smem + (kBwdRowPix + 2) * kPixBytes + dslot * kBwdDyBytes;
+            asm volatile("" : "+r"(dy_addr));
+            if (sy & 1) bwd_crop_row<true>(T, Bm, sh.ylerp[sy], dy_addr, cw);
+            else bwd_crop_row<false>(T, Bm, sh.ylerp[sy], dy_addr, cw);
+        }
+        if (sy & 1) {
+            __syncwarp();
+            const int py = sy >> 1;
+            if (py + kBwdDySlots < kP) stage_bin_row(py + kBwdDySlots, dslot);
+            if (++dslot == kBwdDySlots) {
+                dslot = 0;
+                dphase ^= 1u;
+            }
+        }
+        ++sy;
+    };
+    for (int i = 0; i < n_before; ++i) crop(G0, G1, true);
+#pragma unroll 1
+    for (int k = 0; k < n_rows + 2; k += 2) {
+        // position k (set 0) enters: the row that set 0 held (position k - 2) is complete
+        if (k >= 2 && k - 2 < n_rows) bwd_flush(w, G0, wx, aoff, k - 2, b_pix0, Wf);
+        if (k < n_rows) {
+            prog >>= 1;
+            while (prog & 1ull) {
+                crop(G1, G0, false);  // top row in set 1, bottom (newest) row in set 0
+                prog >>= 1;
+            }
+        }
+        if (k + 1 >= 2 && k - 1 < n_rows) bwd_flush(w, G1, wx, aoff, k - 1, b_pix0, Wf);
+        if (k + 1 < n_rows) {
+            prog >>= 1;
+            while (prog & 1ull) {
+                crop(G0, G1, false);
+                prog >>= 1;
+            }
+        }
+    }
+    for (int i = 0; i < n_after; ++i) crop(G0, G1, true);
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all reduce-adds performed before exit
+}
+
 // Host side: the eight tensor maps of a feature tensor, cached by (pointer, shape).
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encoder(EncodeTiledFn* out) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        FRCNN_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        FRCNN_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, FRCNN_EINVAL,
+                      "roi_pool: cuTensorMapEncodeTiled not available in this driver");
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    *out = encode;
+    return 0;
+}
+
+// row-major [rows, cols] matrix of `esize`-byte elements; box = box_cols x box_rows
+int encode_2d(CUtensorMap* map, const void* ptr, CUtensorMapDataType dt, int esize, long long rows, long long cols, int box_cols,
+              int box_rows) {
+    EncodeTiledFn encode = nullptr;
+    const int rc = get_encoder(&encode);
+    if (rc) return rc;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * esize};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult cr = encode(map, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FRCNN_REQUIRE(cr == CUDA_SUCCESS, FRCNN_EINVAL, "roi_pool: cuTensorMapEncodeTiled failed (CUresult %d)", (int)cr);
+    return 0;
+}
 
 struct MapCacheEntry {
     const void* ptr = nullptr;
@@ -488,35 +869,58 @@ struct MapCacheEntry {
 int get_tensor_maps(const float* feat, long long pixels, int C, int dev, const TensorMaps** out) {
     static thread_local MapCacheEntry cache[16];
     static thread_local int next = 0;
-    static EncodeTiledFn encode = nullptr;
     for (auto& e : cache)
         if (e.ptr == feat && e.pixels == pixels && e.C == C && e.dev == dev) {
             *out = &e.maps;
             return 0;
         }
-    if (!encode) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        FRCNN_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-        FRCNN_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, FRCNN_EINVAL,
-                      "roi_pool_forward: cuTensorMapEncodeTiled not available in this driver");
-        encode = reinterpret_cast<EncodeTiledFn>(fn);
-    }
     MapCacheEntry& e = cache[next];
     next = (next + 1) % 16;
     e.ptr = nullptr;
     for (int i = 0; i < kNumBoxes; ++i) {
-        const cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)pixels};
-        const cuuint64_t strides[1] = {(cuuint64_t)C * sizeof(float)};
-        const cuuint32_t box[2] = {(cuuint32_t)kWarpCh, (cuuint32_t)box_width(i)};
-        const cuuint32_t estr[2] = {1, 1};
-        const CUresult cr = encode(&e.maps.box[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(feat), dims, strides,
-                                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        FRCNN_REQUIRE(cr == CUDA_SUCCESS, FRCNN_EINVAL, "roi_pool_forward: cuTensorMapEncodeTiled failed (CUresult %d)", (int)cr);
+        const int rc = encode_2d(&e.maps.box[i], feat, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pixels, C, kWarpCh, box_width(i));
+        if (rc) return rc;
     }
     e.ptr = feat;
     e.pixels = pixels;
+    e.C = C;
+    e.dev = dev;
+    *out = &e.maps;
+    return 0;
+}
+
+struct BwdCacheEntry {
+    const void *dfeat = nullptr, *dy = nullptr, *codes = nullptr;
+    long long pixels = 0, bins = 0;
+    int C = 0, dev = -1;
+    BwdMaps maps;
+};
+
+int get_bwd_maps(float* dfeat, long long pixels, const float* dy, const unsigned char* codes, long long bins, int C, int dev,
+                 const BwdMaps** out) {
+    static thread_local BwdCacheEntry cache[16];
+    static thread_local int next = 0;
+    for (auto& e : cache)
+        if (e.dfeat == dfeat && e.dy == dy && e.codes == codes && e.pixels == pixels && e.bins == bins && e.C == C && e.dev == dev) {
+            *out = &e.maps;
+            return 0;
+        }
+    BwdCacheEntry& e = cache[next];
+    next = (next + 1) % 16;
+    e.dfeat = nullptr;
+    for (int i = 0; i < kBwdNumBoxes; ++i) {
+        const int rc = encode_2d(&e.maps.dfeat[i], dfeat, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pixels, C, kWarpCh, box_width(i));
+        if (rc) return rc;
+    }
+    int rc = encode_2d(&e.maps.dy, dy, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, bins, C, kWarpCh, kP);
+    if (rc) return rc;
+    rc = encode_2d(&e.maps.codes, codes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, bins, C / 4, kWarpCh / 4, kP);
+    if (rc) return rc;
+    e.dfeat = dfeat;
+    e.dy = dy;
+    e.codes = codes;
+    e.pixels = pixels;
+    e.bins = bins;
     e.C = C;
     e.dev = dev;
     *out = &e.maps;
@@ -556,6 +960,30 @@ int launch_roi_pool_fwd_stream(const float* feat, int B, int Hf, int Wf, int C, 
         else roi_pool_fwd_stream_kernel<0, false><<<grid, kThreads, smem, st>>>(*maps, feat, Hf, Wf, C, r4, R, nchunk, out, nullptr);
     }
     FRCNN_LAUNCH_CHECK("roi_pool_fwd_stream_kernel");
+    return 0;
+}
+
+// dfeat must have been zeroed on the same stream.
+int launch_roi_pool_bwd_stream(int B, int Hf, int Wf, int C, const float* rois, int R, const float* dy,
+                               const unsigned char* codes, float* dfeat, cudaStream_t st) {
+    const size_t smem = (sizeof(BwdShared) + 127) / 128 * 128 + (size_t)kWarps * kBwdWarpBytes;
+    static bool configured[64] = {};
+    int dev = 0;
+    FRCNN_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        FRCNN_CUDA(cudaFuncSetAttribute(roi_pool_bwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    const int nchunk = C / kChunk;
+    FRCNN_REQUIRE((int64_t)R * nchunk < (1ll << 31), FRCNN_ELIMIT, "roi_pool_backward: R * C / 512 too large");
+    FRCNN_REQUIRE((int64_t)B * Hf * Wf < (1ll << 31) && (int64_t)B * R * kP * kP < (1ll << 31), FRCNN_ELIMIT,
+                  "roi_pool_backward: tensor too large");
+    const BwdMaps* maps = nullptr;
+    const int rc = get_bwd_maps(dfeat, (long long)B * Hf * Wf, dy, codes, (long long)B * R * kP * kP, C, dev, &maps);
+    if (rc) return rc;
+    const dim3 grid(R * nchunk, B);
+    roi_pool_bwd_stream_kernel<<<grid, kThreads, smem, st>>>(*maps, Hf, Wf, C, (const float4*)rois, R, nchunk, dy, codes, dfeat);
+    FRCNN_LAUNCH_CHECK("roi_pool_bwd_stream_kernel");
     return 0;
 }
 

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Run one stage a few times on the KITTI batch-8 workload (for ncu captures): bwd | targets | post"""
+"""Run one stage a few times on the KITTI batch-8 workload (for ncu captures): bwd | bwdcodes | targets | post"""
 import importlib, os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
@@ -17,6 +17,10 @@ for _ in range(3):
     if what == "bwd":
         dy = torch.randn((w.batch, w.max_total_size, 7, 7, w.channels), device=dev)
         det.roi_pool_backward(feat, rois, dy, 7, 2)
+    elif what == "bwdcodes":
+        dy = torch.randn((w.batch, w.max_total_size, 7, 7, w.channels), device=dev)
+        _, codes = det.roi_pool_forward_argmax(feat, rois, 7, 2)
+        det.roi_pool_backward_argmax(tuple(feat.shape), rois, dy, codes, 7, 2)
     elif what == "post":
         det.postprocess_output(w.image_shape, anchors, scores, deltas, **w.nms_kwargs(), pre_nms_top_n=w.pre_nms_top_n)
     elif what == "targets":
