@@ -257,11 +257,10 @@ __global__ void __launch_bounds__(kThreads, 2)
     const int r = blockIdx.x / nchunk, ch0 = (blockIdx.x % nchunk) * kChunk, b = blockIdx.y;
     const unsigned full_base = smem_u32(&sh.full[0][0]);
 
+    // Prologue: warp 0 prepares the columns, warp 1 the rows (in parallel), warps 2-3 initialise the mbarriers.
     if (tid < 32) {
         const float4 roi = rois[(size_t)b * R + r];  // x1,y1,x2,y2 (fast_rcnn_detector.py:157-158 reorders for TF)
-        const unsigned all = 0xffffffffu;
-        const Sample xs = sample_axis(roi.x, roi.z, Wf, lane);  // lanes 0..13 are the crop columns / rows
-        const Sample ys = sample_axis(roi.y, roi.w, Hf, lane);
+        const Sample xs = sample_axis(roi.x, roi.z, Wf, lane);  // lanes 0..13 are the crop columns
         // ---- columns: a slot holds the pixels cmin .. cmin + W - 1 of one feature row; a sample outside the map reads
         // a zeroed pixel in front of them: 0 + (p - 0) * 0.
         const Span sp = column_span(xs, lane);
@@ -272,20 +271,32 @@ __global__ void __launch_bounds__(kThreads, 2)
         int W = 0;
 #pragma unroll
         for (int i = 0; i < kNumBoxes; ++i) W = (box == i) ? box_width(i) : W;
-        const bool wide = box >= kNumBoxes || W + first_px > kRingPix;  // does not fit the ring: plain gather path below
-        if (wide && lane < kS) {
-            sh.xlo[lane] = xs.lo; sh.xhi[lane] = xs.hi; sh.xok[lane] = xs.ok; sh.xlerp[lane] = xs.lerp;
-            sh.ylo[lane] = ys.lo; sh.yhi[lane] = ys.hi; sh.yok[lane] = ys.ok;
-        }
+        // does not fit the ring (or no column inside the map at all): plain gather path below
+        const bool wide = box >= kNumBoxes || W + first_px > kRingPix || sp.need == 0;
         if (lane < kS) {
             const int lerp = xs.ok ? __float_as_int(xs.lerp) : 0;
             sh.xt[lane] = make_int4(xs.ok ? (xs.lo - sp.cmin + first_px) * kPixBytes : 0, 0, lerp, lerp);
+            if (wide) {
+                sh.xlo[lane] = xs.lo; sh.xhi[lane] = xs.hi; sh.xok[lane] = xs.ok; sh.xlerp[lane] = xs.lerp;
+            }
         }
+        if (lane == 0) {
+            const int px = W + first_px;
+            sh.box = box;
+            sh.cmin = sp.cmin;
+            sh.first_px = first_px;
+            sh.wide = wide ? 1 : 0;
+            sh.slot_bytes = px * kPixBytes;
+            sh.depth = max(1, min(kMaxDepth, kRingPix / max(px, 1)));
+        }
+    } else if (tid < 64) {
+        const float4 roi = rois[(size_t)b * R + r];
+        const unsigned all = 0xffffffffu;
+        const Sample ys = sample_axis(roi.y, roi.w, Hf, lane);  // lanes 0..13 are the crop rows
         // ---- rows: the downward walk.  The walk stages feature rows in the order rows[0], rows[1], ...; position k
         // goes to register row set k & 1, so the most recently staged row is always the bottom neighbour and the set
-        // it replaces held the old top row.  A crop row is complete when the row at pos[sy] has arrived.
-        const bool anyx = sp.need > 0;
-        const bool v = lane < kS && ys.ok && anyx;
+        // it replaces held the old top row.
+        const bool v = lane < kS && ys.ok;
         const int c = ys.lo;
         const int pv_i = __shfl_up_sync(all, (int)v, 1);  // (collectives first: no short-circuit around a shuffle)
         const bool pv = pv_i != 0 && lane > 0;
@@ -309,23 +320,19 @@ __global__ void __launch_bounds__(kThreads, 2)
         const unsigned prog_lo = __reduce_or_sync(all, (v && bitpos < 32) ? (1u << bitpos) : 0u);
         const unsigned prog_hi = __reduce_or_sync(all, (v && bitpos >= 32) ? (1u << (bitpos - 32)) : 0u);
         const int n_before = __popc(__ballot_sync(all, lane < kS && !v && !(mv & lt)));
-        if (lane < kS) sh.ylerp[lane] = ys.lerp;
+        if (lane < kS) {
+            sh.ylerp[lane] = ys.lerp;
+            sh.ylo[lane] = ys.lo; sh.yhi[lane] = ys.hi; sh.yok[lane] = ys.ok;
+        }
         if (lane == 0) {
-            const int px = W + first_px;
             sh.n_rows = __popc(m1) + __popc(m2);
             sh.prog_lo = prog_lo;
             sh.prog_hi = prog_hi;
             sh.n_before = n_before;
             sh.n_after = kS - n_before - __popc(mv);
-            sh.box = box;
-            sh.cmin = sp.cmin;
-            sh.first_px = first_px;
-            sh.wide = wide ? 1 : 0;
-            sh.slot_bytes = px * kPixBytes;
-            sh.depth = max(1, min(kMaxDepth, kRingPix / max(px, 1)));
         }
-    } else if (tid < 32 + kWarps * kMaxDepth) {
-        mbar_init(full_base + (tid - 32) * 8, 1);
+    } else if (tid < 64 + kWarps * kMaxDepth) {
+        mbar_init(full_base + (tid - 64) * 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
