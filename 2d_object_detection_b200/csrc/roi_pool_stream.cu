@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 //     instruction instead of W x 16 vector atomics.
 // The gradient has no reference summation order (TF: atomics on GPU, a sequential loop on CPU); the bar is 1e-5
 // relative, so contributions are fused multiply-adds and the y-sum is formed before the x-weights are applied.
-// RoIs that do not fit (x-samples more than 25 columns apart) take a plain atomic path.
+// RoIs that do not fit (x-samples more than 29 columns apart) take a plain atomic path.
 // ================================================================================================
 constexpr int kBwdRowPix = 30;                         // per-warp row-buffer ring, pixels
 constexpr int kBwdMaxBufs = 4;
@@ -502,7 +502,8 @@ constexpr int kBwdDySlots = 3;
 constexpr int kBwdDyBytes = kP * kPixBytes;            // 7 bins x 64 channels x 4 B
 constexpr int kBwdCodeBytes = 128;                     // 7 bins x 16 code bytes, padded
 constexpr int kBwdWarpBytes = kBwdRowPix * kPixBytes + 2 * kPixBytes + kBwdDySlots * (kBwdDyBytes + kBwdCodeBytes);
-constexpr int kBwdNumBoxes = 7;                        // box widths 6 .. 26 (box_width(0..6))
+constexpr int kBwdNumBoxes = 8;                        // row-buffer widths 6 .. 26 as in the forward, then the whole ring
+__host__ __device__ constexpr int bwd_box_width(int i) { return i < 7 ? box_width(i) : kBwdRowPix; }
 
 struct BwdMaps {
     CUtensorMap dfeat[kBwdNumBoxes];  // [B*Hf*Wf, C] fp32, box 64 x W: reduce-add target
@@ -648,10 +649,10 @@ __global__ void __launch_bounds__(kThreads, 2)
         const Span sp = column_span(xs, lane);
         int box = 0;
 #pragma unroll
-        for (int i = 0; i < kNumBoxes; ++i) box += (sp.need > box_width(i)) ? 1 : 0;
+        for (int i = 0; i < kBwdNumBoxes; ++i) box += (sp.need > bwd_box_width(i)) ? 1 : 0;
         int W = 0;
 #pragma unroll
-        for (int i = 0; i < kNumBoxes; ++i) W = (box == i) ? box_width(i) : W;
+        for (int i = 0; i < kBwdNumBoxes; ++i) W = (box == i) ? bwd_box_width(i) : W;
         const unsigned xokmask = __ballot_sync(all, lane < kS && xs.ok);
         const bool slow = box >= kBwdNumBoxes;
         if (lane < kS) {
@@ -916,7 +917,7 @@ int get_bwd_maps(float* dfeat, long long pixels, const float* dy, const unsigned
     next = (next + 1) % 16;
     e.dfeat = nullptr;
     for (int i = 0; i < kBwdNumBoxes; ++i) {
-        const int rc = encode_2d(&e.maps.dfeat[i], dfeat, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pixels, C, kWarpCh, box_width(i));
+        const int rc = encode_2d(&e.maps.dfeat[i], dfeat, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pixels, C, kWarpCh, bwd_box_width(i));
         if (rc) return rc;
     }
     int rc = encode_2d(&e.maps.dy, dy, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, bins, C, kWarpCh, kP);

@@ -261,13 +261,16 @@ def test_roi_pool_other_window_sizes_and_out_of_range(det, orc, syn, rng):
 
 
 @pytest.mark.parametrize("grid,C,R,relu", [((24, 78), 256, 30, True), ((6, 9), 64, 9, False), ((7, 5), 3, 5, True),
-                                           ((12, 20), 1024, 12, True), ((9, 11), 512, 8, False)])
+                                           ((12, 20), 1024, 12, True), ((9, 11), 512, 8, False), ((24, 78), 512, 48, True)])
 def test_roi_pool_backward(det, orc, syn, rng, grid, C, R, relu):
     f = syn.feature_maps(rng, 2, grid, C, relu=relu)
     rois = syn.random_rois(rng, 2, R, num_valid=[R - 3, R])
     rois[1, 0] = [0.0, 0.0, 1.0, 1.0]          # whole map: 4-row bin-rows, right neighbour beyond the last column
     rois[1, 1] = [0.9, 0.8, 0.1, 0.2]          # flipped box: cells walk right to left
     rois[1, 2] = [-0.2, 0.3, 0.4, 1.3]         # partly outside: zero-filled samples can win the max
+    if R >= 40:                                # every row-buffer width of the streaming backward, up to the atomic path
+        w = np.linspace(0.0, 0.6, 24, dtype=F)
+        rois[0, :24] = np.stack([0.45 - w / 2, np.full_like(w, 0.1), 0.45 + w / 2, np.full_like(w, 0.9)], -1)
     dy = rng.standard_normal((2, R, 7, 7, C)).astype(F)
     ref = orc.roi_pool_backward(f, rois, dy, 7, 2)
     got = host(det.roi_pool_backward(dev(f), dev(rois), dev(dy), 7, 2))
