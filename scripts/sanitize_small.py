@@ -16,6 +16,9 @@ rois_abs = det.to_absolute(out["pred_boxes"], image_shape)
 sc7 = torch.softmax(torch.randn(2, 50, 8, device="cuda"), -1).contiguous()
 dl7 = (torch.randn(2, 50, 7, 4, device="cuda") * 0.1).contiguous()
 det.postprocess_output(image_shape, rois_abs, sc7, dl7, 0.0, 0.6, 10, 30)
+special = torch.tensor([[0.0, 0.0, 1.0, 1.0], [0.9, 0.8, 0.1, 0.2], [-0.2, 0.3, 0.4, 1.3], [-0.5, -0.6, -0.1, -0.2], [0.5, 0.5, 0.5, 0.5]],
+                       device="cuda")
+out["pred_boxes"][1, :5] = special  # whole map, reversed, partly / completely outside, degenerate: every RoI-pool path
 for C in (1024, 256, 6):
     feat = torch.as_tensor(syn.feature_maps(rng, 2, grid, C)).cuda().requires_grad_(True)
     pooled = det.ROIPooling(7, 2)(feat, out["pred_boxes"], True, True)
