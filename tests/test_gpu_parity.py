@@ -385,3 +385,30 @@ def test_full_size_properties_kitti_b8(det, orc, syn):
     assert torch.equal(again["kept_indices"], out["kept_indices"]) and torch.equal(again["pred_boxes"], out["pred_boxes"])
     # bit-exact pooled features for one image against the oracle at full width
     np.testing.assert_array_equal(host(pooled[3]), orc.roi_pool_forward(f[3:4], host(out["pred_boxes"])[3:4], 7, 2)[0])
+
+
+def test_full_size_backward_properties_kitti_b8(det, orc, syn):
+    """BASELINE size (8 x 300 RoIs x 1024 channels): the streaming backward (arg-max codes, TMA reduce-add) against the
+    independent recompute kernel, conservation of gradient mass per channel, linearity in dY, and the oracle on one image."""
+    w, anchors, scores, deltas, _ = _decoded(orc, syn, "kitti_b8", 8, 777)
+    out = det.postprocess_output(w.image_shape, dev(anchors), dev(scores), dev(deltas), **w.nms_kwargs())
+    rois = out["pred_boxes"]
+    f = syn.feature_maps(np.random.default_rng(2), 8, w.grid, 1024)
+    ft = dev(f)
+    dy = torch.randn((8, 300, 7, 7, 1024), device="cuda")
+    pooled, codes = det.roi_pool_forward_argmax(ft, rois, 7, 2)
+    assert torch.equal(pooled, det.roi_pool_forward(ft, rois, 7, 2))  # the two forward variants agree bit for bit
+    g_codes = det.roi_pool_backward_argmax(tuple(ft.shape), rois, dy, codes, 7, 2)
+    g_walk = det.roi_pool_backward(ft, rois, dy, 7, 2)
+    scale = float(g_walk.abs().max())
+    assert float((g_codes - g_walk).abs().max()) <= 2e-5 * scale
+    # proposals are clipped to the image, every sample lies inside the map: all of dY arrives somewhere (weights sum to 1)
+    mass_in = dy.double().sum(dim=(1, 2, 3))
+    mass_out = g_codes.double().sum(dim=(1, 2))
+    assert float((mass_in - mass_out).abs().max()) <= 1e-4 * float(dy.double().abs().sum(dim=(1, 2, 3)).max())
+    # linear in dY
+    g2 = det.roi_pool_backward_argmax(tuple(ft.shape), rois, 2.0 * dy, codes, 7, 2)
+    assert float((g2 - 2.0 * g_codes).abs().max()) <= 2e-5 * 2.0 * scale
+    # the oracle on one image
+    ref = orc.roi_pool_backward(f[5:6], host(rois)[5:6], host(dy)[5:6], 7, 2)[0]
+    np.testing.assert_allclose(host(g_codes[5]), ref, rtol=RTOL, atol=RTOL * np.abs(ref).max())
