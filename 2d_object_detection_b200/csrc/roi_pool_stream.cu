@@ -3,9 +3,10 @@
 //
 // CTA = one RoI x 512 channels, 8 warps; a warp owns 64 channels (one float2 per lane; 128 registers, 2 CTAs per SM)
 // and runs its OWN copy pipeline -- after the prologue the warps never synchronise with each other.
-//   * Prologue (warp 0, registers + shuffles): the feature columns [cmin, cmax] under the 14 x-samples select one of
-//     eight TMA tensor maps (box = 64 channels x W pixels, W >= the span); the 14 y-samples become the list of feature
-//     rows the downward walk needs, in order, and per crop row the walk position that completes it.
+//   * Prologue (registers + shuffles; warp 0 the columns, warp 1 the rows, in parallel): the feature columns
+//     [cmin, cmax] under the 14 x-samples select one of eight TMA tensor maps (box = 64 channels x W pixels, W >= the
+//     span); the 14 y-samples become the list of feature rows the downward walk needs, in order, and a 64-bit bit
+//     string that says after which staged row each crop row is complete.
 //   * Staging: ONE cp.async.bulk.tensor per feature row and warp (box of W consecutive pixels x 64 channels of the
 //     [B*Hf*Wf, C] view of the NHWC maps) into slot `k % depth` of the warp's private shared-memory ring, completion
 //     on the slot's mbarrier.  The ring depth adapts to the RoI: narrow RoIs (small boxes) get a deep ring.  When a
@@ -362,8 +363,8 @@ __global__ void __launch_bounds__(kThreads, 2)
         const u64 one = pack2(onef, onef);
         const float* fb = feat + (size_t)b * Hf * Wf * C + ch0 + tid * 2;
         float2* ob = reinterpret_cast<float2*>(out + ((size_t)b * R + r) * (kP * kP) * C + ch0) + tid;
-#pragma unroll 1
         unsigned char* cb = kCodes ? codes + ((size_t)b * R + r) * (kP * kP) * (C / 4) + (ch0 + tid * 2) / 4 : nullptr;
+#pragma unroll 1
         for (int bin = 0; bin < kP * kP; ++bin) {
             const int py = bin / kP, px = bin - py * kP;
             float2 best = make_float2(0.0f, 0.0f);

@@ -130,7 +130,11 @@ FRCNN_API int frcnn_nms(const float* boxes, const float* scores, int segments, i
 /* ---- models/detectors/fast_rcnn_detector.py:133-177 ROIPooling ------------------------------
  * tf.image.crop_and_resize to (P*k)x(P*k) (bilinear, (H-1) scaling, extrapolation 0) fused with
  * MaxPool2D(k) (stride k, VALID).  feature_maps [B,Hf,Wf,C] NHWC; rois [B,R,4] rel x1,y1,x2,y2;
- * out [B,R,P,P,C] (== [B,R,P*P*C] flattened in (py,px,c) order).  P*k <= 32. */
+ * out [B,R,P,P,C] (== [B,R,P*P*C] flattened in (py,px,c) order).  P*k <= 32.
+ * The reference configuration (pooled_size 7, kernel_size 2, C % 512 == 0) runs the row-streaming TMA kernel
+ * (roi_pool_stream.cu); it builds CUtensorMap descriptors of feature_maps on the host (cached per pointer and shape,
+ * cuTensorMapEncodeTiled through cudaGetDriverEntryPoint), so feature_maps must stay valid until the stream has run.
+ * Other shapes run the bin-row walk / generic kernels (roi_pool.cu).  All variants give identical bits. */
 FRCNN_API int frcnn_roi_pool_forward(const float* feature_maps, int B, int Hf, int Wf, int C, const float* rois, int R,
                            int pooled_size, int kernel_size, float* out, frcnn_stream_t stream);
 
@@ -144,7 +148,9 @@ FRCNN_API int frcnn_roi_pool_backward(const float* feature_maps, int B, int Hf, 
 /* Training-mode pair: the forward additionally writes the per-channel arg-max of every 2x2 window as 2-bit codes
  * (argmax_codes [B,R,P,P,C/4] bytes, four codes per float4 of channels), the backward consumes them and needs neither
  * the feature maps nor a second interpolation pass.  Same results as the two functions above.
- * Supported when frcnn_roi_pool_argmax_supported returns 1: C % 4 == 0, kernel_size == 2, pooled_size <= 8. */
+ * Supported when frcnn_roi_pool_argmax_supported returns 1: C % 4 == 0, kernel_size == 2, pooled_size <= 8.
+ * In the reference configuration both run on the row-streaming walk; the backward adds whole feature-row segments to
+ * dfeature with TMA reduce-add (cp.reduce.async.bulk.tensor), so dfeature needs the usual 16-byte alignment only. */
 FRCNN_API int frcnn_roi_pool_argmax_supported(int C, int pooled_size, int kernel_size);
 FRCNN_API int frcnn_roi_pool_forward_argmax(const float* feature_maps, int B, int Hf, int Wf, int C, const float* rois, int R,
                                   int pooled_size, int kernel_size, float* out, unsigned char* argmax_codes,
