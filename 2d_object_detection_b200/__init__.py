@@ -31,7 +31,7 @@ from .pipeline import ProposalRoIPipeline  # noqa: E402
 from .utils.boxes import clip_to_window, decode, encode, to_absolute, to_relative  # noqa: E402
 from .utils.metrics import area, intersection, iou  # noqa: E402
 from .utils.post_processing import decode_filter, non_max_suppression, postprocess_output  # noqa: E402
-from .utils.training import (generate_targets, generate_targets_batched, get_sample_indices,  # noqa: E402
+from .utils.training import (generate_targets, generate_targets_batched, get_sample_indices, sample_and_gather_batched,  # noqa: E402
                              rpn_objectness_labels)
 
 __version__ = "0.1.0"

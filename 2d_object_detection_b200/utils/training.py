@@ -1,7 +1,8 @@
 """Drop-in for the reference's utils/training.py: ``generate_targets`` (single image, the signature the
 reference calls inside tf.map_fn) and ``generate_targets_batched`` (the natural GPU form: all images in
-two kernel launches).  ``get_sample_indices`` follows the reference's sampling rule with torch's Philox
-generator (the reference uses unseeded tf.random, so parity is statistical -- SURVEY 8(f) rank 2).
+two kernel launches).  ``get_sample_indices`` / ``sample_and_gather_batched`` follow the reference's sampling rule in one
+hand-written kernel with counter-based Philox draws (the reference uses unseeded tf.random, so parity is
+distributional -- SURVEY 8(f) rank 2).
 """
 from __future__ import annotations
 
@@ -56,17 +57,72 @@ def rpn_objectness_labels(gt_labels):
     return torch.nn.functional.one_hot(s.clamp(0, 1), 2).to(torch.float32) * inside
 
 
-def get_sample_indices(target_labels, num_samples, foreground_proportion, generator=None):
-    """utils/training.py:80-120 for one image: up to round(num_samples*foreground_proportion) foregrounds without
-    replacement (shuffle), the rest backgrounds WITH replacement (uniform draws), concatenated fg first."""
+_seed_counter = [0]
+
+
+def _next_seed(generator=None, seed=None) -> int:
+    """A fresh 64-bit seed per call: explicit ``seed``, else derived from the generator's (or torch's) initial seed and a
+    call counter, so that successive calls draw different samples while a re-seeded run repeats itself."""
+    if seed is not None:
+        return int(seed) & 0xFFFFFFFFFFFFFFFF
+    base = int(generator.initial_seed()) if generator is not None else int(torch.initial_seed())
+    _seed_counter[0] += 1
+    return (base * 0x9E3779B97F4A7C15 + _seed_counter[0] * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
+
+
+def sample_and_gather_batched(target_labels, num_samples, foreground_proportion, pred_scores=None, target_boxes=None,
+                              pred_boxes=None, generator=None, seed=None, check_background=True):
+    """utils/training.py:80-120 for all images at once, fused with the four tf.gather(batch_dims=1) of
+    rpn_detector.py:151-160 / fast_rcnn_detector.py:121-130: ONE kernel launch (block-wide compaction of the foreground /
+    background lists, Philox keys, bitonic selection, row gathers).
+
+    target_labels [B,N,nc+1] (+ optionally pred_scores [B,N,nc+1], target_boxes / pred_boxes [B,N,nc,4]).  Returns a dict
+    with "indices" [B,num_samples] int64, "counts" [B,2] int32 (#foreground, #background) and, for every tensor given, its
+    sampled rows under the reference's key ("target_labels", "pred_scores", "target_boxes", "pred_boxes").
+    ``check_background`` reads the counts back (one synchronisation) and raises where the reference would."""
     tl = as_device(target_labels)
-    nonzero = tl.sum(-1) != 0.0
-    fg = torch.nonzero(nonzero & (tl[:, 0] == 0.0)).reshape(-1)
-    bg = torch.nonzero(nonzero & (tl[:, 0] == 1.0)).reshape(-1)
-    n_fg = min(int(fg.numel()), int(round(num_samples * foreground_proportion)))
-    n_bg = int(num_samples) - n_fg
-    fg = fg[torch.randperm(fg.numel(), device=tl.device, generator=generator)][:n_fg]
-    if bg.numel() == 0 and n_bg > 0:
-        raise ValueError("no background region to sample from")  # the reference's tf.random.uniform fails here too
-    draw = torch.randint(0, max(int(bg.numel()), 1), (n_bg,), device=tl.device, generator=generator)
-    return torch.cat([fg, bg[draw]], 0)
+    if tl.dim() != 3:
+        raise ValueError(f"target_labels must be [B,N,nc+1], got {tuple(tl.shape)}")
+    B, N, L = tl.shape
+    S = int(num_samples)
+    if L < 2 or S <= 0 or not (0.0 <= float(foreground_proportion) <= 1.0):
+        raise ValueError("need nc >= 1, num_samples > 0 and 0 <= foreground_proportion <= 1")
+    dev = tl.device
+    srcs, outs = {}, {}
+    for name, t, shape in (("pred_scores", pred_scores, (B, N, L)), ("target_boxes", target_boxes, (B, N, L - 1, 4)),
+                           ("pred_boxes", pred_boxes, (B, N, L - 1, 4))):
+        if t is not None:
+            t = as_device(t)
+            if tuple(t.shape) != shape:
+                raise ValueError(f"{name} must be {shape}, got {tuple(t.shape)}")
+            srcs[name] = t
+            outs[name] = torch.empty((B, S) + shape[2:], dtype=torch.float32, device=dev)
+    outs["target_labels"] = torch.empty((B, S, L), dtype=torch.float32, device=dev)
+    idx = torch.empty((B, S), dtype=torch.int64, device=dev)
+    counts = torch.empty((B, 2), dtype=torch.int32, device=dev)
+    Lb = lib()
+    ws_bytes = Lb.frcnn_sample_indices_workspace_bytes(B, N)
+    ws = workspace(ws_bytes)
+    check(Lb.frcnn_sample_and_gather(ptr(tl), B, N, L, S, float(foreground_proportion), _next_seed(generator, seed), ptr(idx),
+                                     ptr(counts), ptr(srcs.get("pred_scores")), ptr(srcs.get("target_boxes")),
+                                     ptr(srcs.get("pred_boxes")), ptr(outs["target_labels"]), ptr(outs.get("pred_scores")),
+                                     ptr(outs.get("target_boxes")), ptr(outs.get("pred_boxes")), ptr(ws), ws_bytes, stream()),
+          "sample_and_gather")
+    if check_background:
+        c = counts.cpu()
+        quota = int(round(S * float(foreground_proportion)))
+        need_bg = S - torch.clamp(c[:, 0], max=quota)
+        if bool(((c[:, 1] == 0) & (need_bg > 0)).any()):
+            raise ValueError("no background region to sample from")  # the reference's tf.random.uniform fails here too
+    outs["indices"] = idx
+    outs["counts"] = counts
+    return outs
+
+
+def get_sample_indices(target_labels, num_samples, foreground_proportion, generator=None, seed=None):
+    """utils/training.py:80-120 for one image ([N,nc+1] -> [num_samples] int64): up to round(num_samples *
+    foreground_proportion) foregrounds without replacement, the rest backgrounds WITH replacement, foregrounds first."""
+    tl = as_device(target_labels)
+    if tl.dim() != 2:
+        raise ValueError(f"target_labels must be [N,nc+1], got {tuple(tl.shape)}")
+    return sample_and_gather_batched(tl[None], num_samples, foreground_proportion, generator=generator, seed=seed)["indices"][0]

@@ -173,6 +173,25 @@ FRCNN_API int frcnn_generate_targets(const float* gt_labels, const float* gt_box
                            float* max_iou, int32_t* argmax, void* workspace, size_t workspace_bytes,
                            frcnn_stream_t stream);
 
+/* ---- utils/training.py:80-120 get_sample_indices, batched, fused with the tf.gather(batch_dims=1) calls that follow
+ * it (models/detectors/rpn_detector.py:151-160, fast_rcnn_detector.py:121-130) --------------------------------------
+ *   target_labels [B,N,nc+1].  foreground = non-zero label row with background column 0, background = non-zero row
+ *   with background column 1 (both in ascending index order, as tf.where lists them).
+ *   n_fg = min(#foreground, round(num_samples * foreground_proportion)); n_fg foregrounds without replacement
+ *   (shuffle + prefix), num_samples - n_fg backgrounds with replacement; indices [B,num_samples] int64 = fg then bg.
+ *   The reference draws from TensorFlow's unseeded generator: parity is distributional.  Here every draw is a pure
+ *   function of (seed, image, position) through Philox4x32-10, so a call is reproducible.
+ *   counts [B,2] int32 = (#foreground, #background) per image (nullable).  An image that needs a background draw but has
+ *   no background region gets index -1 there (the reference raises); callers check counts.
+ *   Optional gathers (any of the four outputs may be NULL): out_labels / out_scores [B,num_samples,nc+1] from
+ *   target_labels / pred_scores, out_target_boxes / out_pred_boxes [B,num_samples,nc,4] from target_boxes / pred_boxes. */
+FRCNN_API size_t frcnn_sample_indices_workspace_bytes(int B, int N);
+FRCNN_API int frcnn_sample_and_gather(const float* target_labels, int B, int N, int num_classes_plus_1, int num_samples,
+                            float foreground_proportion, uint64_t seed, int64_t* indices, int32_t* counts,
+                            const float* pred_scores, const float* target_boxes, const float* pred_boxes,
+                            float* out_labels, float* out_scores, float* out_target_boxes, float* out_pred_boxes,
+                            void* workspace, size_t workspace_bytes, frcnn_stream_t stream);
+
 /* ---- host-buffer pipeline: FasterRCNN.call inference slice, models/faster_rcnn.py:52-55 ------
  * postprocess_output(rpn) -> ROIPooling on the proposals, taking and returning HOST buffers
  * (pinned memory recommended).  Owns its device buffers and streams; run() copies inputs host->device,

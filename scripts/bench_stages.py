@@ -81,6 +81,9 @@ def main():
         glt, gbt = torch.as_tensor(gl).to(dev), torch.as_tensor(gb).to(dev)
         ms = timeit(lambda: det.generate_targets_batched(obj, gbt, valid, w.image_shape, [0.7, 1.0], [0.0, 0.3]), flush=flush)
         report("generate_targets RPN (N_valid x 100)", wname, ms, 40 * valid.shape[0] * B, {"N_valid": int(valid.shape[0])})
+        tl_rpn, tb_rpn = det.generate_targets_batched(obj, gbt, valid, w.image_shape, [0.7, 1.0], [0.0, 0.3])
+        ms = timeit(lambda: det.sample_and_gather_batched(tl_rpn, 256, 0.5, target_boxes=tb_rpn, seed=1, check_background=False), flush=flush)
+        report("sample_and_gather RPN (256 of N_valid, labels + box targets)", wname, ms, B * (8 * valid.shape[0] + 256 * (8 + 8 + 16 + 16)))
         # RCNN-stage postprocess (7 classes, per-class cap 100, cross-class merge to 300): SURVEY 8(f) rank 1
         lg = torch.randn((B, R, 8), device=dev) * 1.5
         sc7 = torch.softmax(lg, -1).contiguous()

@@ -2,6 +2,7 @@
 """Training-path step of BASELINE.json configs[4], one process per GPU:
 
     postprocess_output (RPN proposals)  ->  generate_targets RPN (N_valid x 100) + RCNN (300 x G')
+    ->  sample_and_gather (256 / 64 training samples per image, fused with the gathers)
     ->  ROIPooling forward with saved arg-max codes  ->  ROIPooling backward (dY -> dFeature)
     ->  ncclAllReduce(sum, fp32) of a synthetic weight-gradient buffer (34.2 MB backbone, 51.0 MB with the heads)
 
@@ -65,9 +66,12 @@ def main():
         sc, dl, feat, gl, gb = sets[i % n_sets]
         out = det.postprocess_output(w.image_shape, valid, sc, dl, **kw)                     # no pre-NMS cap (reference)
         obj = det.rpn_objectness_labels(gl)
-        det.generate_targets_batched(obj, gb, valid, w.image_shape, [0.7, 1.0], [0.0, 0.3])  # RPN targets
+        tl, tb = det.generate_targets_batched(obj, gb, valid, w.image_shape, [0.7, 1.0], [0.0, 0.3])  # RPN targets
+        det.sample_and_gather_batched(tl, 256, 0.5, sc, tb, dl, seed=i, check_background=False)     # RPN minibatch (no sync)
         rois = out["pred_boxes"]
-        det.generate_targets_batched(gl, gb, det.to_absolute(rois, w.image_shape), w.image_shape, [0.5, 1.0], [0.0, 0.5])
+        tl2, tb2 = det.generate_targets_batched(gl, gb, det.to_absolute(rois, w.image_shape), w.image_shape, [0.5, 1.0],
+                                                [0.0, 0.5])
+        det.sample_and_gather_batched(tl2, 64, 0.25, target_boxes=tb2, seed=i, check_background=False)  # RCNN minibatch
         pooled, codes = det.roi_pool_forward_argmax(feat, rois, 7, 2)
         if world > 1:                                                                        # weight gradients of the step
             comm.wait_stream(torch.cuda.current_stream())
@@ -108,7 +112,7 @@ def main():
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps({
-            "metric": "training-path images/s (proposals + target matching + RoI pool fwd/bwd + weight-gradient all-reduce)",
+            "metric": "training-path images/s (proposals + target matching + sampling + RoI pool fwd/bwd + weight-gradient all-reduce)",
             "value": B * world / (ms * 1e-3), "unit": "images/s", "n_gpus": world, "ms_per_step": ms, "per_gpu_batch": B,
             "scaling": "weak", "N_valid": int(valid.shape[0]), "allreduce_mb": args.grad_mb, "allreduce_alone_ms": ar_ms,
             "config": "kitti 375x1242 training mode (anchors inside the image, no pre-NMS cap), 100 padded gt boxes, "

@@ -349,6 +349,70 @@ def test_get_sample_indices_rule(det, rng):
     assert ((idx[40:] >= 100) & (idx[40:] < 900)).all()
 
 
+def test_sample_and_gather_batched_rule_and_distribution(det, rng):
+    """utils/training.py:80-120 + the gathers of rpn_detector.py:155-160, batched.  The reference draws from an unseeded
+    generator, so the checks are the rule (which regions may appear where, how many, no repeats among foregrounds), the
+    gathers (bit-exact against torch.gather), reproducibility per seed, and the distributions of the draws."""
+    B, N, nc, S = 3, 9000, 7, 64
+    L = nc + 1
+    tl = np.zeros((B, N, L), F)
+    fg_sets, bg_sets = [], []
+    for b, n_fg in enumerate((5, 16, 5000)):  # fewer than / exactly / far more than the quota of round(64 * 0.25) = 16
+        perm = rng.permutation(N)
+        fg, bg = np.sort(perm[:n_fg]), np.sort(perm[n_fg:n_fg + 3000])  # the remaining rows are all-zero: ignored
+        tl[b, fg, 1 + rng.integers(0, nc, n_fg)] = 1
+        tl[b, bg, 0] = 1
+        fg_sets.append(set(fg.tolist()))
+        bg_sets.append(set(bg.tolist()))
+    ps = rng.standard_normal((B, N, L)).astype(F)
+    tb = rng.standard_normal((B, N, nc, 4)).astype(F)
+    pb = rng.standard_normal((B, N, nc, 4)).astype(F)
+    out = det.sample_and_gather_batched(dev(tl), S, 0.25, dev(ps), dev(tb), dev(pb), seed=1234)
+    idx, counts = host(out["indices"]), host(out["counts"])
+    assert idx.shape == (B, S) and idx.dtype == np.int64
+    for b, n_fg_all in enumerate((5, 16, 5000)):
+        n_fg = min(n_fg_all, 16)
+        assert counts[b].tolist() == [n_fg_all, 3000]
+        assert set(idx[b, :n_fg].tolist()) <= fg_sets[b] and len(set(idx[b, :n_fg].tolist())) == n_fg
+        assert set(idx[b, n_fg:].tolist()) <= bg_sets[b]
+    gi = torch.as_tensor(idx).cuda()
+    for key, src in (("target_labels", tl), ("pred_scores", ps)):
+        ref = torch.gather(dev(src), 1, gi[..., None].expand(-1, -1, L))
+        assert torch.equal(out[key], ref)
+    for key, src in (("target_boxes", tb), ("pred_boxes", pb)):
+        ref = torch.gather(dev(src), 1, gi[..., None, None].expand(-1, -1, nc, 4))
+        assert torch.equal(out[key], ref)
+    # same seed -> same sample; another seed -> another one
+    again = det.sample_and_gather_batched(dev(tl), S, 0.25, seed=1234)
+    other = det.sample_and_gather_batched(dev(tl), S, 0.25, seed=1235)
+    assert torch.equal(again["indices"], out["indices"]) and not torch.equal(other["indices"], out["indices"])
+    # distributions: 40 foregrounds, quota 8 -> each is chosen with probability 1/5; 50 backgrounds drawn uniformly
+    N2, trials = 200, 400
+    t2 = np.zeros((trials, N2, 2), F)
+    t2[:, :40, 1] = 1
+    t2[:, 100:150, 0] = 1
+    d = host(det.sample_and_gather_batched(dev(t2), 32, 0.25, seed=99)["indices"])  # every image gets its own draws
+    fg_hits = np.bincount(d[:, :8].ravel(), minlength=N2)[:40]
+    bg_hits = np.bincount(d[:, 8:].ravel(), minlength=N2)[100:150]
+    assert fg_hits.sum() == trials * 8 and bg_hits.sum() == trials * 24
+    chi_fg = ((fg_hits - trials * 8 / 40) ** 2 / (trials * 8 / 40)).sum()  # 39 degrees of freedom: 99.9 % quantile 72
+    chi_bg = ((bg_hits - trials * 24 / 50) ** 2 / (trials * 24 / 50)).sum()  # 49 degrees of freedom: 99.9 % quantile 85
+    assert chi_fg < 80 and chi_bg < 95, (chi_fg, chi_bg)
+    first = np.bincount(d[:, 0], minlength=N2)[:40]  # the FIRST foreground slot is uniform too (a shuffle, not a sorted subset)
+    assert ((first - trials / 40) ** 2 / (trials / 40)).sum() < 80
+    # an image that needs background draws but has none: the reference raises
+    t3 = np.zeros((1, 10, 2), F)
+    t3[0, :3, 1] = 1
+    with pytest.raises(ValueError):
+        det.sample_and_gather_batched(dev(t3), 8, 0.5)
+    # more foregrounds than one sort pass holds (chunked selection): still distinct foregrounds only
+    t4 = np.zeros((1, 20000, 2), F)
+    t4[0, :, 1] = 1
+    t4[0, ::7, :] = [1, 0]
+    i4 = host(det.sample_and_gather_batched(dev(t4), 256, 0.5, seed=5)["indices"])[0]
+    assert len(set(i4[:128].tolist())) == 128 and (i4[:128] % 7 != 0).all() and (i4[128:] % 7 == 0).all()
+
+
 # ------------------------------------------------------------------ host-buffer pipeline == device API
 def test_host_pipeline_matches_device_api(det, orc, syn):
     w, anchors, scores, deltas, _ = _decoded(orc, syn, "kitti_b8", 2, 11)
