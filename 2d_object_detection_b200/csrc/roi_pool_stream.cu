@@ -664,10 +664,9 @@ __global__ void __launch_bounds__(kThreads, 2)
     const unsigned dfull_base = smem_u32(&sh.dfull[0][0]);
     const unsigned all = 0xffffffffu;
 
-    if (tid < 32) {
+    if (tid < 32) {  // warp 0: the columns
         const float4 roi = rois[(size_t)b * R + r];
         const Sample xs = sample_axis(roi.x, roi.z, Wf, lane);
-        const Sample ys = sample_axis(roi.y, roi.w, Hf, lane);
         const Span sp = column_span(xs, lane);
         int box = 0;
 #pragma unroll
@@ -676,16 +675,27 @@ __global__ void __launch_bounds__(kThreads, 2)
 #pragma unroll
         for (int i = 0; i < kBwdNumBoxes; ++i) W = (box == i) ? bwd_box_width(i) : W;
         const unsigned xokmask = __ballot_sync(all, lane < kS && xs.ok);
-        const bool slow = box >= kBwdNumBoxes;
+        const bool slow = box >= kBwdNumBoxes || sp.need == 0;  // too wide for a row buffer, or no column inside the map
         if (lane < kS) {
             const int lerp = xs.ok ? __float_as_int(xs.lerp) : 0;
             sh.xt[lane] = make_int4(xs.ok ? (xs.lo - sp.cmin) * kPixBytes : 0, 0, lerp, lerp);
             sh.xlo[lane] = xs.lo; sh.xhi[lane] = xs.hi; sh.xok[lane] = xs.ok; sh.xlerp[lane] = xs.lerp;
+        }
+        if (lane == 0) {
+            sh.xokmask = xokmask;
+            sh.box = box;
+            sh.cmin = sp.cmin;
+            sh.W = W;
+            sh.nbufs = max(1, min(kBwdMaxBufs, kBwdRowPix / max(W, 1)));
+            sh.slow = slow ? 1 : 0;
+        }
+    } else if (tid < 64) {  // warp 1: the downward walk, exactly as in the forward kernel
+        const float4 roi = rois[(size_t)b * R + r];
+        const Sample ys = sample_axis(roi.y, roi.w, Hf, lane);
+        if (lane < kS) {
             sh.ylo[lane] = ys.lo; sh.yhi[lane] = ys.hi; sh.yok[lane] = ys.ok; sh.ylerp[lane] = ys.lerp;
         }
-        // the downward walk, exactly as in the forward kernel
-        const bool anyx = sp.need > 0;
-        const bool v = lane < kS && ys.ok && anyx;
+        const bool v = lane < kS && ys.ok;
         const int c = ys.lo;
         const int pv_i = __shfl_up_sync(all, (int)v, 1);
         const bool pv = pv_i != 0 && lane > 0;
@@ -712,17 +722,11 @@ __global__ void __launch_bounds__(kThreads, 2)
             sh.n_rows = __popc(m1) + __popc(m2);
             sh.prog_lo = prog_lo;
             sh.prog_hi = prog_hi;
-            sh.xokmask = xokmask;
             sh.n_before = n_before;
             sh.n_after = kS - n_before - __popc(mv);
-            sh.box = box;
-            sh.cmin = sp.cmin;
-            sh.W = W;
-            sh.nbufs = max(1, min(kBwdMaxBufs, kBwdRowPix / max(W, 1)));
-            sh.slow = slow ? 1 : 0;
         }
-    } else if (tid < 32 + kWarps * kBwdDySlots) {
-        mbar_init(dfull_base + (tid - 32) * 8, 1);
+    } else if (tid < 64 + kWarps * kBwdDySlots) {
+        mbar_init(dfull_base + (tid - 64) * 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -799,19 +803,22 @@ __global__ void __launch_bounds__(kThreads, 2)
     u64 G0[kS], G1[kS];
 #pragma unroll
     for (int i = 0; i < kS; ++i) G0[i] = G1[i] = 0ull;
-    int sy = 0, dslot = 0;
-    unsigned dphase = 0;
+    int sy = 0, dslot = 0, cw_py = -1;
+    unsigned dphase = 0, cw = 0u;  // cw: this lane's 2-bit arg-max codes (2 channels x 7 bins) of bin-row cw_py
     // One crop row: wait for its bin-row's dY, accumulate (unless it lies outside the map), release the slot after the
     // second row of the bin-row and re-arm it with the bin-row three further down.
     auto crop = [&](u64 (&T)[kS], u64 (&Bm)[kS], bool outside) {
         mbar_wait(w.dfull0 + dslot * 8, dphase);
         if (!outside) {
-            unsigned cw = 0u;
+            if (cw_py != (sy >> 1)) {  // first crop row of this bin-row that lies inside the map
+                cw = 0u;
 #pragma unroll
-            for (int j = 0; j < kP; ++j) {
-                unsigned byte;
-                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(byte) : "r"(code_slots + dslot * kBwdCodeBytes + j * 16 + (lane >> 1)));
-                cw |= ((byte >> ((lane & 1) * 4)) & 15u) << (4 * j);
+                for (int j = 0; j < kP; ++j) {
+                    unsigned byte;
+                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(byte) : "r"(code_slots + dslot * kBwdCodeBytes + j * 16 + (lane >> 1)));
+                    cw |= ((byte >> ((lane & 1) * 4)) & 15u) << (4 * j);
+                }
+                cw_py = sy >> 1;
             }
             unsigned dy_addr = w.lane_smem + (kBwdRowPix + 2) * kPixBytes + dslot * kBwdDyBytes;
             asm volatile("" : "+r"(dy_addr));
