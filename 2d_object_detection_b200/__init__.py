@@ -6,7 +6,8 @@ The sub-packages mirror the reference's module paths so the path drops into ``fa
     utils.boxes            clip_to_window, decode, encode, to_absolute, to_relative
     utils.metrics          area, intersection, iou
     utils.post_processing  postprocess_output  (+ stage functions decode_filter, non_max_suppression)
-    utils.training         generate_targets, generate_targets_batched, get_sample_indices
+    utils.training         generate_targets, generate_targets_batched, get_sample_indices, sample_and_gather_batched
+    utils.losses           ClassificationLoss, RegressionLoss, sampled_losses
     models.detectors.rpn_detector        generate_anchors, valid_anchor_indices, RPNAnchors
     models.detectors.fast_rcnn_detector  ROIPooling (differentiable)
     pipeline               ProposalRoIPipeline (host buffers in, host buffers out)
@@ -31,6 +32,7 @@ from .pipeline import ProposalRoIPipeline  # noqa: E402
 from .utils.boxes import clip_to_window, decode, encode, to_absolute, to_relative  # noqa: E402
 from .utils.metrics import area, intersection, iou  # noqa: E402
 from .utils.post_processing import decode_filter, non_max_suppression, postprocess_output  # noqa: E402
+from .utils.losses import ClassificationLoss, RegressionLoss, sampled_losses  # noqa: E402
 from .utils.training import (generate_targets, generate_targets_batched, get_sample_indices, sample_and_gather_batched,  # noqa: E402
                              rpn_objectness_labels)
 

@@ -173,6 +173,19 @@ FRCNN_API int frcnn_generate_targets(const float* gt_labels, const float* gt_box
                            float* max_iou, int32_t* argmax, void* workspace, size_t workspace_bytes,
                            frcnn_stream_t stream);
 
+/* ---- utils/losses.py:4-43 on the sampled rows (models/faster_rcnn.py:87-101), forward + gradients ------------------
+ *   ClassificationLoss: Keras CategoricalCrossentropy on probabilities (normalise by the row sum, clip to
+ *   [1e-7, 1 - 1e-7], -sum t log c, mean over the `rows` rows); target_labels / pred_scores [rows, nc+1].
+ *   RegressionLoss: Huber(delta 1) per coordinate, mean over the 4 coordinates, SUMMED over the rows whose target box is
+ *   non-zero; target_boxes / pred_boxes [box_rows, 4].
+ *   losses[0] = classification, losses[1] = regression, losses[2] = number of regression rows kept (device, 3 floats).
+ *   d_pred_scores [rows, nc+1] / d_pred_boxes [box_rows, 4] (nullable) receive grad_cls * dL_cls/dp and
+ *   grad_reg * dL_reg/dp.  One CTA, fixed summation order (deterministic); 1e-5 relative vs the reference's reductions. */
+FRCNN_API int frcnn_sampled_losses(const float* target_labels, const float* pred_scores, int64_t rows, int num_classes_plus_1,
+                         const float* target_boxes, const float* pred_boxes, int64_t box_rows, float grad_cls,
+                         float grad_reg, float* losses, float* d_pred_scores, float* d_pred_boxes,
+                         frcnn_stream_t stream);
+
 /* ---- utils/training.py:80-120 get_sample_indices, batched, fused with the tf.gather(batch_dims=1) calls that follow
  * it (models/detectors/rpn_detector.py:151-160, fast_rcnn_detector.py:121-130) --------------------------------------
  *   target_labels [B,N,nc+1].  foreground = non-zero label row with background column 0, background = non-zero row

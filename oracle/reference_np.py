@@ -283,3 +283,26 @@ def generate_targets(gt_labels, gt_boxes, regions, image_shape, foreground_iou_i
     mask = tl[:, 1:] != 0
     tb[mask] = np.broadcast_to(enc[:, None, :], (N, nc, 4))[mask]
     return tl, tb
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# utils/losses.py:4-43.  tf.keras.losses.CategoricalCrossentropy() on probabilities and
+# tf.keras.losses.Huber(reduction=NONE) with the reference's row filter; float32 element arithmetic, float64 only for
+# the final reductions (Eigen's reduction order is unspecified: compare within 1e-5).
+def classification_loss(target_labels, pred_scores):
+    t = np.asarray(target_labels, np.float32).reshape(-1, np.shape(target_labels)[-1])
+    p = np.asarray(pred_scores, np.float32).reshape(t.shape)
+    q = p / p.sum(-1, keepdims=True, dtype=np.float32)             # Keras rescales probabilities to sum to 1
+    c = np.clip(q, np.float32(1e-7), np.float32(1.0) - np.float32(1e-7))  # backend.epsilon()
+    rows = -(t * np.log(c)).sum(-1, dtype=np.float64)
+    return float(rows.mean())                                       # Reduction.SUM_OVER_BATCH_SIZE
+
+
+def regression_loss(target_boxes, pred_boxes):
+    t = np.asarray(target_boxes, np.float32).reshape(-1, 4)
+    p = np.asarray(pred_boxes, np.float32).reshape(-1, 4)
+    keep = t.sum(-1, dtype=np.float32) != 0.0                      # utils/losses.py:36-38
+    e = p[keep] - t[keep]
+    a = np.abs(e)
+    h = np.where(a <= 1.0, np.float32(0.5) * e * e, a - np.float32(0.5))  # Huber, delta = 1
+    return float(h.mean(-1, dtype=np.float64).sum())                # mean over the 4 coordinates, SUM over the rows

@@ -2,7 +2,7 @@
 """Training-path step of BASELINE.json configs[4], one process per GPU:
 
     postprocess_output (RPN proposals)  ->  generate_targets RPN (N_valid x 100) + RCNN (300 x G')
-    ->  sample_and_gather (256 / 64 training samples per image, fused with the gathers)
+    ->  sample_and_gather (256 / 64 training samples per image, fused with the gathers) -> sampled losses (RPN)
     ->  ROIPooling forward with saved arg-max codes  ->  ROIPooling backward (dY -> dFeature)
     ->  ncclAllReduce(sum, fp32) of a synthetic weight-gradient buffer (34.2 MB backbone, 51.0 MB with the heads)
 
@@ -67,7 +67,8 @@ def main():
         out = det.postprocess_output(w.image_shape, valid, sc, dl, **kw)                     # no pre-NMS cap (reference)
         obj = det.rpn_objectness_labels(gl)
         tl, tb = det.generate_targets_batched(obj, gb, valid, w.image_shape, [0.7, 1.0], [0.0, 0.3])  # RPN targets
-        det.sample_and_gather_batched(tl, 256, 0.5, sc, tb, dl, seed=i, check_background=False)     # RPN minibatch (no sync)
+        smp = det.sample_and_gather_batched(tl, 256, 0.5, sc, tb, dl, seed=i, check_background=False)  # RPN minibatch (no sync)
+        det.sampled_losses(smp["target_labels"], smp["pred_scores"], smp["target_boxes"], smp["pred_boxes"])  # rpn_cls, rpn_reg
         rois = out["pred_boxes"]
         tl2, tb2 = det.generate_targets_batched(gl, gb, det.to_absolute(rois, w.image_shape), w.image_shape, [0.5, 1.0],
                                                 [0.0, 0.5])

@@ -503,3 +503,45 @@ def test_engine_step_is_cuda_graph_capturable(det, orc, syn):
     g.replay()
     torch.cuda.synchronize()
     assert torch.equal(eng.pooled, eager[1] * 2.0)  # scaling by a power of two is exact through lerps and max
+
+
+def test_sampled_losses_forward_and_gradients(det, rng):
+    """utils/losses.py:4-43 on sampled rows: the kernel against the NumPy restatement (1e-5) and, for the gradients,
+    against torch autograd through an independent composite of the same formulas."""
+    from oracle import reference_np as ref
+    B, S, nc = 4, 64, 7
+    L = nc + 1
+    t_lab = np.zeros((B, S, L), F)
+    t_lab[np.arange(B)[:, None], np.arange(S)[None, :], rng.integers(0, L, (B, S))] = 1
+    logits = rng.standard_normal((B, S, L)).astype(F) * 3
+    p = np.exp(logits - logits.max(-1, keepdims=True))
+    p = (p / p.sum(-1, keepdims=True)).astype(F)
+    p[0, 0] = [1, 0, 0, 0, 0, 0, 0, 0]            # exact 0 / 1 probabilities: clipped at 1e-7, no gradient through the clip
+    p[0, 1] *= 0.5                                 # a row that does not sum to 1: Keras renormalises
+    t_box = np.zeros((B, S, nc, 4), F)
+    fg = rng.random((B, S, nc)) < 0.1
+    t_box[fg] = rng.standard_normal((int(fg.sum()), 4)).astype(F)
+    p_box = (t_box + rng.standard_normal(t_box.shape).astype(F) * 1.5).astype(F)  # errors on both sides of delta = 1
+    ps, pb = dev(p).requires_grad_(True), dev(p_box).requires_grad_(True)
+    cls, reg = det.sampled_losses(dev(t_lab), ps, dev(t_box), pb)
+    np.testing.assert_allclose(cls.item(), ref.classification_loss(t_lab, p), rtol=RTOL)
+    np.testing.assert_allclose(reg.item(), ref.regression_loss(t_box, p_box), rtol=RTOL)
+    (2.0 * cls + 0.5 * reg).backward()
+    # independent composite in torch (float64 reductions)
+    ps2, pb2 = dev(p).double().requires_grad_(True), dev(p_box).double().requires_grad_(True)
+    q = ps2 / ps2.sum(-1, keepdim=True)
+    c = torch.clamp(q, 1e-7, 1 - 1e-7)
+    cls2 = -(dev(t_lab).double() * torch.log(c)).sum(-1).mean()
+    keep = dev(t_box).sum(-1) != 0
+    e = (pb2 - dev(t_box).double())[keep]
+    h = torch.where(e.abs() <= 1, 0.5 * e * e, e.abs() - 0.5)
+    reg2 = h.mean(-1).sum()
+    (2.0 * cls2 + 0.5 * reg2).backward()
+    np.testing.assert_allclose(cls.item(), cls2.item(), rtol=RTOL)
+    np.testing.assert_allclose(host(ps.grad), host(ps2.grad.float()), rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(host(pb.grad), host(pb2.grad.float()), rtol=1e-5, atol=1e-8)
+    # the reference's class interface
+    assert det.ClassificationLoss()(dev(t_lab), dev(p)).item() == cls.item()
+    assert det.RegressionLoss()(dev(t_box), dev(p_box)).item() == reg.item()
+    # no kept row: regression loss 0 (the reference's reduce_sum over an empty tensor)
+    assert float(det.RegressionLoss()(torch.zeros(2, 8, 1, 4, device="cuda"), torch.ones(2, 8, 1, 4, device="cuda"))) == 0.0

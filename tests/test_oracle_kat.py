@@ -402,3 +402,20 @@ def test_synthetic_scores_unique(syn, rng):
     for b in range(2):
         assert np.unique(s[b, :, 1]).size == 16848
     assert (s[..., 1] > 0).all() and (s[..., 1] < 1).all()
+
+
+def test_losses_known_answers():
+    """utils/losses.py:4-43, hand-computed: CCE of a one-hot target against [0.5, 0.5] is ln 2, Keras
+    renormalises rows and clips at 1e-7; Huber(delta 1) is quadratic up to |e| = 1, averaged over the 4 coordinates and
+    SUMMED over the rows with a non-zero target."""
+    t = np.array([[[0, 1], [1, 0]]], np.float32)
+    assert abs(rnp.classification_loss(t, np.array([[[0.5, 0.5], [0.5, 0.5]]], np.float32)) - np.log(2.0)) < 1e-6
+    assert abs(rnp.classification_loss(t, np.array([[[1.0, 1.0], [3.0, 3.0]]], np.float32)) - np.log(2.0)) < 1e-6  # renormalised
+    clipped = rnp.classification_loss(np.array([[[0, 1]]], np.float32), np.array([[[1.0, 0.0]]], np.float32))
+    assert abs(clipped - (-np.log(np.float32(1e-7)))) < 1e-4                                          # -log(eps) = 16.118
+    # rows 2 and 3 are filtered out: the reference keeps a row iff the SUM of its target is non-zero (utils/losses.py:36),
+    # so a non-zero target that sums to zero is dropped too
+    tb = np.array([[[[1, 1, 1, 1]], [[0, 0, 0, 0]], [[2, -2, 0, 0]], [[0, 0, 0, 3]]]], np.float32)
+    pb = np.array([[[[1.5, 1, 3, 1]], [[9, 9, 9, 9]], [[2, -2, 0, 1]], [[0, 0, 0, 3.5]]]], np.float32)
+    assert abs(rnp.regression_loss(tb, pb) - ((0.125 + 0 + 1.5 + 0) / 4 + 0.125 / 4)) < 1e-6         # 0.40625 + 0.03125
+    assert rnp.regression_loss(np.zeros((1, 2, 1, 4), np.float32), np.ones((1, 2, 1, 4), np.float32)) == 0.0
