@@ -107,6 +107,18 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
         : "memory");
 #endif
 }
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+
 // box (c0 = first channel, c1 = first pixel) of the [pixels, channels] view -> shared memory, completion on `bar`
 __device__ __forceinline__ void tma_box_g2s(unsigned dst, const CUtensorMap* map, int c0, int c1, unsigned bar) {
     asm volatile(
@@ -440,17 +452,20 @@ __global__ void __launch_bounds__(kThreads, 2)
     float2* optr = reinterpret_cast<float2*>(out + ((size_t)b * R + r) * (kP * kP) * C + ch0) + tid;
     const int bin_stride = C / 2;  // float2 per bin
     int sy = 0;
+    float yl_next = sh.ylerp[0];  // the y weight of the next crop row, loaded one crop row ahead
     unsigned cw = 0u;  // kCodes: the 2-bit window positions of this lane's two channels for the 7 bins of the bin-row
     unsigned char* cptr = kCodes ? codes + ((size_t)b * R + r) * (kP * kP) * (C / 4) + (ch0 + tid * 2) / 4 : nullptr;
     // One finished crop row: fold it into the bin maxima; after the second row of a bin-row store the 7 bins.
     auto emit = [&](const u64 (&T)[kS], const u64 (&Bm)[kS], bool outside) {
+        const float yl = yl_next;
+        yl_next = sh.ylerp[min(sy + 1, kS - 1)];
         if (!(sy & 1)) {
             cw = 0u;
             if (outside) {  // crop row outside the map: extrapolation value 0 takes part in the max
 #pragma unroll
                 for (int j = 0; j < kP; ++j) M[j] = make_float2(0.0f, 0.0f);
             } else {
-                crop_row<true, kCodes>(T, Bm, sh.ylerp[sy], w.one, M, cw);
+                crop_row<true, kCodes>(T, Bm, yl, w.one, M, cw);
             }
         } else {
             if (outside) {
@@ -464,7 +479,7 @@ __global__ void __launch_bounds__(kThreads, 2)
                     }
                 }
             } else {
-                crop_row<false, kCodes>(T, Bm, sh.ylerp[sy], w.one, M, cw);
+                crop_row<false, kCodes>(T, Bm, yl, w.one, M, cw);
             }
 #pragma unroll
             for (int j = 0; j < kP; ++j) __stcs(optr + j * bin_stride, M[j]);
@@ -892,18 +907,6 @@ struct PersistShared {
     unsigned long long tab_full[2], tab_empty[2];
     unsigned long long full[kWarps][kPSlots];
 };
-
-__device__ __forceinline__ void mbar_arrive(unsigned bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_test(unsigned bar, unsigned parity) {
-    unsigned ok;
-    asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                 : "=r"(ok)
-                 : "r"(bar), "r"(parity)
-                 : "memory");
-    return ok != 0;
-}
 
 // Tables of the next item (one warp): fetch its index, then the same column / row analysis as the prologue above.
 __device__ __forceinline__ void persist_make_tables(Park* pk, unsigned* counter, int n_items, int nchunk, int R, int Hf, int Wf,
