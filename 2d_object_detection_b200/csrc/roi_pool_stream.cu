@@ -820,9 +820,12 @@ __global__ void __launch_bounds__(kThreads, 2)
     for (int i = 0; i < kS; ++i) G0[i] = G1[i] = 0ull;
     int sy = 0, dslot = 0, cw_py = -1;
     unsigned dphase = 0, cw = 0u;  // cw: this lane's 2-bit arg-max codes (2 channels x 7 bins) of bin-row cw_py
+    float yl_next = sh.ylerp[0];   // the y weight of the next crop row, loaded one crop row ahead
     // One crop row: wait for its bin-row's dY, accumulate (unless it lies outside the map), release the slot after the
     // second row of the bin-row and re-arm it with the bin-row three further down.
     auto crop = [&](u64 (&T)[kS], u64 (&Bm)[kS], bool outside) {
+        const float yl = yl_next;
+        yl_next = sh.ylerp[min(sy + 1, kS - 1)];
         mbar_wait(w.dfull0 + dslot * 8, dphase);
         if (!outside) {
             if (cw_py != (sy >> 1)) {  // first crop row of this bin-row that lies inside the map
@@ -837,8 +840,8 @@ __global__ void __launch_bounds__(kThreads, 2)
             }
             unsigned dy_addr = w.lane_smem + (kBwdRowPix + 2) * kPixBytes + dslot * kBwdDyBytes;
             asm volatile("" : "+r"(dy_addr));
-            if (sy & 1) bwd_crop_row<true>(T, Bm, sh.ylerp[sy], dy_addr, cw);
-            else bwd_crop_row<false>(T, Bm, sh.ylerp[sy], dy_addr, cw);
+            if (sy & 1) bwd_crop_row<true>(T, Bm, yl, dy_addr, cw);
+            else bwd_crop_row<false>(T, Bm, yl, dy_addr, cw);
         }
         if (sy & 1) {
             __syncwarp();
