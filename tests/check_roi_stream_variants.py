@@ -1,7 +1,7 @@
 """Quick bit-exactness check of the RoI forward against the oracle on awkward RoIs (default: row-streaming kernel;
 FRCNN_FWD_PERSIST=1: persistent variant; FRCNN_FWD_WALK=1: bin-row walk).  Test infrastructure, like tests/."""
 import sys, importlib, os, numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # tests/ -> repo root; sys.path.insert(0, ROOT)
 det = importlib.import_module('2d_object_detection_b200'); syn = det.synthetic
 import oracle
 rng = np.random.default_rng(0)
