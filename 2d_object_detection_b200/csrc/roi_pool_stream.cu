@@ -553,7 +553,7 @@ struct BwdShared {
     float ylerp[kS];
     int rows[2 * kS];
     int n_rows, box, cmin, W, nbufs, slow;
-    unsigned prog_lo, prog_hi, xokmask;  // xokmask bit i: crop column i lies inside the map
+    unsigned prog_lo, prog_hi, xpair;  // xpair: 3 bits per bin = how its two crop columns relate (see bwd_flush)
     int n_before, n_after;
     int xlo[kS], xhi[kS], xok[kS], ylo[kS], yhi[kS], yok[kS];  // plain sample tables for the slow path
     float xlerp[kS];
@@ -598,7 +598,8 @@ struct BwdWalk {
     unsigned lane_smem;   // warp_smem + this lane's channel offset
     unsigned dfull0;      // shared address of this warp's dfull[0]
     int warp_ch, W, nbufs, buf, buf_off, issued;
-    unsigned xok;         // bit i: crop column i lies inside the map
+    unsigned xpair;       // 3 bits per bin: 0 both columns in the same cell, 1 second column one cell to the right,
+                          // 2 both inside the map but further apart, 3 only the first inside, 4 only the second, 5 none
 };
 
 // One crop row inside the map: route dY of its 7 bins to the samples that won the max, weight by (1 - yl) / yl.
@@ -643,17 +644,48 @@ __device__ __forceinline__ void bwd_flush(BwdWalk& w, u64 (&G)[kS], const float 
     asm volatile("" : "+r"(buf));  // keep the address in a register (ptxas otherwise rebuilds it from %tid for every sample)
 #pragma unroll 2
     for (int p = 0; p < w.W; ++p) sts64(buf + p * kPixBytes, 0ull);
+    // One bin (two crop columns a, b) at a time.  When both columns sit in the same cell or in neighbouring cells -- the
+    // common cases -- their pixels are distinct addresses, so the loads of the pair go out together and the chain of
+    // dependent shared-memory round trips is 7 long instead of 14; the per-pixel order of additions is unchanged.
+    auto one = [&](int i) {
+        const float xl = wx[i];
+        const float xr = fsub(1.0f, xl);
+        const unsigned a = buf + aoff[i];
+        const u64 lo = lds64(a), hi = lds64(a + kPixBytes);
+        sts64(a, fma2(G[i], pack2(xr, xr), lo));
+        sts64(a + kPixBytes, fma2(G[i], pack2(xl, xl), hi));
+    };
 #pragma unroll
-    for (int i = 0; i < kS; ++i) {
-        if ((w.xok >> i) & 1u) {  // samples outside the map receive no gradient (uniform branch)
-            const float xl = wx[i];
-            const float xr = fsub(1.0f, xl);
-            const unsigned a = buf + aoff[i];
-            const u64 lo = lds64(a), hi = lds64(a + kPixBytes);
-            sts64(a, fma2(G[i], pack2(xr, xr), lo));
-            sts64(a + kPixBytes, fma2(G[i], pack2(xl, xl), hi));
+    for (int j = 0; j < kP; ++j) {
+        const unsigned pc = (w.xpair >> (3 * j)) & 7u;  // warp-uniform
+        const int ia = 2 * j, ib = 2 * j + 1;
+        if (pc <= 1u) {
+            const float xla = wx[ia], xlb = wx[ib];
+            const u64 wa1 = pack2(xla, xla), wb1 = pack2(xlb, xlb);
+            const float xra = fsub(1.0f, xla), xrb = fsub(1.0f, xlb);
+            const u64 wa0 = pack2(xra, xra), wb0 = pack2(xrb, xrb);
+            const unsigned a = buf + aoff[ia];
+            if (pc == 0u) {  // same cell: two pixels
+                u64 p0 = lds64(a), p1 = lds64(a + kPixBytes);
+                p0 = fma2(G[ib], wb0, fma2(G[ia], wa0, p0));
+                p1 = fma2(G[ib], wb1, fma2(G[ia], wa1, p1));
+                sts64(a, p0);
+                sts64(a + kPixBytes, p1);
+            } else {  // neighbouring cells: three pixels
+                u64 p0 = lds64(a), p1 = lds64(a + kPixBytes), p2 = lds64(a + 2 * kPixBytes);
+                p0 = fma2(G[ia], wa0, p0);
+                p1 = fma2(G[ib], wb0, fma2(G[ia], wa1, p1));
+                p2 = fma2(G[ib], wb1, p2);
+                sts64(a, p0);
+                sts64(a + kPixBytes, p1);
+                sts64(a + 2 * kPixBytes, p2);
+            }
+        } else {  // further apart, or a column outside the map (which receives no gradient)
+            if (pc == 2u || pc == 3u) one(ia);
+            if (pc == 2u || pc == 4u) one(ib);
         }
-        G[i] = 0ull;
+        G[ia] = 0ull;
+        G[ib] = 0ull;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the TMA engine
     __syncwarp();
@@ -689,7 +721,10 @@ __global__ void __launch_bounds__(kThreads, 2)
         int W = 0;
 #pragma unroll
         for (int i = 0; i < kBwdNumBoxes; ++i) W = (box == i) ? bwd_box_width(i) : W;
-        const unsigned xokmask = __ballot_sync(all, lane < kS && xs.ok);
+        // how the two crop columns of a bin relate (lane 2j holds the first column of bin j, lane 2j + 1 the second)
+        const int lo_n = __shfl_down_sync(all, xs.lo, 1), ok_n = __shfl_down_sync(all, (int)xs.ok, 1);
+        const unsigned pcode = (!xs.ok && !ok_n) ? 5u : !ok_n ? 3u : !xs.ok ? 4u : lo_n == xs.lo ? 0u : lo_n == xs.lo + 1 ? 1u : 2u;
+        const unsigned xpair = __reduce_or_sync(all, (lane < kS && !(lane & 1)) ? (pcode << (3 * (lane >> 1))) : 0u);
         const bool slow = box >= kBwdNumBoxes || sp.need == 0;  // too wide for a row buffer, or no column inside the map
         if (lane < kS) {
             const int lerp = xs.ok ? __float_as_int(xs.lerp) : 0;
@@ -697,7 +732,7 @@ __global__ void __launch_bounds__(kThreads, 2)
             sh.xlo[lane] = xs.lo; sh.xhi[lane] = xs.hi; sh.xok[lane] = xs.ok; sh.xlerp[lane] = xs.lerp;
         }
         if (lane == 0) {
-            sh.xokmask = xokmask;
+            sh.xpair = xpair;
             sh.box = box;
             sh.cmin = sp.cmin;
             sh.W = W;
@@ -789,7 +824,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     w.buf = 0;
     w.buf_off = 0;
     w.issued = 0;
-    w.xok = __reduce_or_sync(all, sh.xokmask);
+    w.xpair = __reduce_or_sync(all, sh.xpair);
     const int n_rows = __reduce_or_sync(all, sh.n_rows);
     const int b_pix0 = b * Hf * Wf;
     const unsigned dy_slots = w.warp_smem + (kBwdRowPix + 2) * kPixBytes;
