@@ -65,7 +65,7 @@ __global__ void score_keys_kernel(const float* __restrict__ scores, int64_t n, f
 // Stage 2: segmented greedy NMS.
 // ------------------------------------------------------------------------------------------------
 constexpr int kNmsThreads = 1024;
-constexpr int kChunk = 512;          // candidates ordered + resolved per iteration
+constexpr int kChunk = 1024;         // candidates ordered + resolved per iteration (one per thread in the sort)
 constexpr int kBins = 2048;          // 11-bit radix digits
 
 // TF CombinedNMS IOU on corner-normalised boxes with precomputed areas; returns iou > thr.
@@ -145,9 +145,12 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
             S->pfx = 0;
             S->pmask = 0;
             const int budget = S->budget;
-            S->want_max = min(kChunk, budget);
+            // chunk target: 512 candidates when at most 512 boxes are kept (a select + sort round then costs about what
+            // its greedy blocks do), the full 1024 for larger caps (dense-anchor configurations need fewer rounds)
+            const int target = cap > kChunk / 2 ? kChunk : kChunk / 2;
+            S->want_max = min(target, budget);
             // exact count only when pre_nms_top_n ends inside this chunk; otherwise any size in [half, full] will do
-            S->want_min = budget <= kChunk ? S->want_max : kChunk / 2;
+            S->want_min = budget <= target ? S->want_max : target / 2;
             S->need = S->want_max;
             S->select_done = 0;
             S->expect = 0;
