@@ -545,3 +545,39 @@ def test_sampled_losses_forward_and_gradients(det, rng):
     assert det.RegressionLoss()(dev(t_box), dev(p_box)).item() == reg.item()
     # no kept row: regression loss 0 (the reference's reduce_sum over an empty tensor)
     assert float(det.RegressionLoss()(torch.zeros(2, 8, 1, 4, device="cuda"), torch.ones(2, 8, 1, 4, device="cuda"))) == 0.0
+
+
+def test_roi_stream_kernels_vs_walk_kernels_random_shapes(det):
+    """Randomised cross-check of the two independent RoI implementations on shapes the oracle tests do not enumerate:
+    C = 512 takes the row-streaming TMA kernels, the same tensor split into two 256-channel halves takes the bin-row walk
+    kernels.  Forward and arg-max codes must agree bit for bit, the gradients to 1e-5 (different summation orders)."""
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    rs = np.random.default_rng(99)
+    for it in range(24):
+        B, R = int(rs.integers(1, 4)), int(rs.integers(1, 40))
+        Hf, Wf = int(rs.integers(1, 61)), int(rs.integers(1, 131))
+        f = torch.randn((B, Hf, Wf, 512), device="cuda", generator=g)
+        if it % 2:
+            f = torch.relu(f)  # exact zeros: arg-max ties (T8)
+        c = torch.rand((B, R, 2), device="cuda", generator=g)
+        wh = torch.rand((B, R, 2), device="cuda", generator=g) ** 2 * (1.6 if it % 3 == 0 else 0.7)
+        rois = torch.cat([c - wh / 2, c + wh / 2], -1)  # x1,y1,x2,y2; some reach outside [0,1]
+        if it % 4 == 0:
+            rois = rois.clamp(0.0, 1.0)
+        if it % 5 == 0:
+            rois[:, : max(1, R // 4)] = 0.0  # zero padding (T7)
+        rois = rois.contiguous()
+        halves = [f[..., :256].contiguous(), f[..., 256:].contiguous()]
+        out = det.roi_pool_forward(f, rois, 7, 2)
+        ref = torch.cat([det.roi_pool_forward(h, rois, 7, 2) for h in halves], -1)
+        assert torch.equal(out, ref), (it, B, R, Hf, Wf)
+        out_a, codes = det.roi_pool_forward_argmax(f, rois, 7, 2)
+        assert torch.equal(out_a, out)
+        codes_ref = torch.cat([det.roi_pool_forward_argmax(h, rois, 7, 2)[1] for h in halves], -1)
+        assert torch.equal(codes, codes_ref), (it, B, R, Hf, Wf)
+        dy = torch.randn(out.shape, device="cuda", generator=g)
+        gs = det.roi_pool_backward_argmax(tuple(f.shape), rois, dy, codes, 7, 2)
+        gw = torch.cat([det.roi_pool_backward(h, rois, dy[..., i * 256:(i + 1) * 256].contiguous(), 7, 2)
+                        for i, h in enumerate(halves)], -1)
+        tol = 2e-5 * max(float(gw.abs().max()), 1e-6)
+        assert float((gs - gw).abs().max()) <= tol, (it, B, R, Hf, Wf)
