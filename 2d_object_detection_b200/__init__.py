@@ -4,7 +4,7 @@ The sub-packages mirror the reference's module paths so the path drops into ``fa
 ``train_faster_rcnn.py``:
 
     utils.boxes            clip_to_window, decode, encode, to_absolute, to_relative
-    utils.metrics          area, intersection, iou
+    utils.metrics          area, intersection, iou, AveragePrecision, MeanAveragePrecision
     utils.post_processing  postprocess_output  (+ stage functions decode_filter, non_max_suppression)
     utils.training         generate_targets, generate_targets_batched, get_sample_indices, sample_and_gather_batched
     utils.losses           ClassificationLoss, RegressionLoss, sampled_losses
@@ -30,7 +30,7 @@ from .models.detectors.rpn_detector import (RPNAnchors, generate_anchors,  # noq
                                             remove_invalid_anchors_and_predictions, valid_anchor_indices)
 from .pipeline import ProposalRoIPipeline  # noqa: E402
 from .utils.boxes import clip_to_window, decode, encode, to_absolute, to_relative  # noqa: E402
-from .utils.metrics import area, intersection, iou  # noqa: E402
+from .utils.metrics import AveragePrecision, MeanAveragePrecision, area, intersection, iou  # noqa: E402
 from .utils.post_processing import decode_filter, non_max_suppression, postprocess_output  # noqa: E402
 from .utils.losses import ClassificationLoss, RegressionLoss, sampled_losses  # noqa: E402
 from .utils.training import (generate_targets, generate_targets_batched, get_sample_indices, sample_and_gather_batched,  # noqa: E402

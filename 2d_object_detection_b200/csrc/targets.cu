@@ -178,3 +178,63 @@ int frcnn_generate_targets(const float* gt_labels, const float* gt_boxes, int B,
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Average-precision matching: utils/metrics.py:57-84 AveragePrecision.update_state_single_image, batched over images
+// (SURVEY 8(f) rank 4).  Ground-truth rows whose coordinates sum to 0 are padding (:67-68); every remaining gt box
+// marks the prediction of highest IoU with it (tf.math.argmax: the first maximum) as a true positive when that IoU
+// exceeds the threshold (:79-83).  IoU is the reference's own (utils/metrics.py:183-208), never materialised as a
+// matrix.  One CTA per image, one warp per gt box.
+// ------------------------------------------------------------------------------------------------
+namespace frcnn {
+
+__global__ void __launch_bounds__(256)
+    ap_match_kernel(const float4* __restrict__ gt_boxes, int G, const float4* __restrict__ pred_boxes, int M, float iou_thr,
+                    int32_t* __restrict__ true_pos, int32_t* __restrict__ num_gt) {
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    __shared__ int count;
+    if (threadIdx.x == 0) count = 0;
+    int32_t* tp = true_pos + (size_t)b * M;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) tp[i] = 0;
+    __syncthreads();
+    const float4* gt = gt_boxes + (size_t)b * G;
+    const float4* pr = pred_boxes + (size_t)b * M;
+    for (int g = warp; g < G; g += nwarps) {
+        const float4 gb = gt[g];
+        if (fadd(fadd(fadd(gb.x, gb.y), gb.z), gb.w) == 0.0f) continue;  // padding row
+        if (lane == 0) atomicAdd(&count, 1);
+        float best = -1.0f;
+        int arg = 0x7fffffff;
+        for (int i = lane; i < M; i += 32) {
+            const float v = ref_iou(gb, pr[i]);
+            if (v > best) {  // ascending i per lane: keeps the first maximum of the lane
+                best = v;
+                arg = i;
+            }
+        }
+        for (int d = 16; d > 0; d >>= 1) {  // warp arg-max, lower index on ties (tf.math.argmax)
+            const float ob = __shfl_xor_sync(0xffffffffu, best, d);
+            const int oa = __shfl_xor_sync(0xffffffffu, arg, d);
+            if (ob > best || (ob == best && oa < arg)) {
+                best = ob;
+                arg = oa;
+            }
+        }
+        if (lane == 0 && M > 0 && best > iou_thr) tp[arg] = 1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && num_gt) num_gt[b] = count;
+}
+
+}  // namespace frcnn
+
+extern "C" int frcnn_ap_match(const float* gt_boxes, int B, int G, const float* pred_boxes, int M, float iou_threshold,
+                              int32_t* true_positives, int32_t* num_gt, frcnn_stream_t stream) {
+    FRCNN_REQUIRE(B > 0 && G >= 0 && M >= 0 && B <= 65535, FRCNN_EINVAL, "ap_match: bad shape");
+    FRCNN_REQUIRE(aligned16(gt_boxes) && aligned16(pred_boxes) && (true_positives || M == 0), FRCNN_EINVAL,
+                  "ap_match: box tensors must be 16-byte aligned");
+    frcnn::ap_match_kernel<<<B, 256, 0, frcnn::as_stream(stream)>>>((const float4*)gt_boxes, G, (const float4*)pred_boxes, M,
+                                                                     iou_threshold, true_positives, num_gt);
+    FRCNN_LAUNCH_CHECK("ap_match_kernel");
+    return 0;
+}

@@ -173,6 +173,13 @@ FRCNN_API int frcnn_generate_targets(const float* gt_labels, const float* gt_box
                            float* max_iou, int32_t* argmax, void* workspace, size_t workspace_bytes,
                            frcnn_stream_t stream);
 
+/* ---- utils/metrics.py:57-84 AveragePrecision.update_state_single_image, batched ------------------------------------
+ *   gt_boxes [B,G,4] (rows summing to 0 = padding), pred_boxes [B,M,4]; true_positives [B,M] int32: 1 where the
+ *   prediction is the highest-IoU prediction (first maximum) of at least one ground-truth box and that IoU exceeds
+ *   iou_threshold; num_gt [B] int32 = ground-truth boxes after padding removal (nullable).  IoU as in frcnn_iou_*. */
+FRCNN_API int frcnn_ap_match(const float* gt_boxes, int B, int G, const float* pred_boxes, int M, float iou_threshold,
+                   int32_t* true_positives, int32_t* num_gt, frcnn_stream_t stream);
+
 /* ---- utils/losses.py:4-43 on the sampled rows (models/faster_rcnn.py:87-101), forward + gradients ------------------
  *   ClassificationLoss: Keras CategoricalCrossentropy on probabilities (normalise by the row sum, clip to
  *   [1e-7, 1 - 1e-7], -sum t log c, mean over the `rows` rows); target_labels / pred_scores [rows, nc+1].

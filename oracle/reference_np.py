@@ -306,3 +306,45 @@ def regression_loss(target_boxes, pred_boxes):
     a = np.abs(e)
     h = np.where(a <= 1.0, np.float32(0.5) * e * e, a - np.float32(0.5))  # Huber, delta = 1
     return float(h.mean(-1, dtype=np.float64).sum())                # mean over the 4 coordinates, SUM over the rows
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# utils/metrics.py:4-84 AveragePrecision, restated for one stream of updates.
+def _iou_ref(a, b):
+    """utils/metrics.py:150-208 on two boxes (float32)."""
+    F = np.float32
+    iw = max(F(0), F(min(a[2], b[2]) - max(a[0], b[0])))
+    ih = max(F(0), F(min(a[3], b[3]) - max(a[1], b[1])))
+    inter = F(iw * ih)
+    if inter == 0:
+        return F(0)
+    area_a = F(F(a[2] - a[0]) * F(a[3] - a[1]))
+    area_b = F(F(b[2] - b[0]) * F(b[3] - b[1]))
+    return F(inter / F(F(area_a + area_b) - inter))
+
+
+def ap_true_positives(gt_boxes, pred_boxes, iou_threshold):
+    """update_state_single_image (:57-84): -> (true_positives [M] int32, number of non-padding gt boxes)."""
+    gt = np.asarray(gt_boxes, np.float32)
+    pb = np.asarray(pred_boxes, np.float32)
+    gt = gt[gt.sum(-1, dtype=np.float32) != 0.0]
+    tp = np.zeros(len(pb), np.int32)
+    for g in gt:
+        ious = np.array([_iou_ref(g, p) for p in pb], np.float32)
+        if len(ious):
+            j = int(np.argmax(ious))                         # first maximum, like tf.math.argmax
+            if ious[j] > np.float32(iou_threshold):
+                tp[j] = 1
+    return tp, len(gt)
+
+
+def average_precision(true_pos, scores, true_count, num_points=11):
+    """result() (:25-42) for the concatenated state."""
+    true_pos, scores = np.asarray(true_pos), np.asarray(scores, np.float32)
+    order = np.argsort(-scores, kind="stable")
+    cum_tp = np.cumsum(true_pos[order]).astype(np.float32)
+    cum_pos = (np.arange(len(scores)) + 1).astype(np.float32)
+    precisions = np.concatenate([cum_tp / cum_pos, [np.float32(0.0)]]).astype(np.float32)
+    recalls = np.concatenate([cum_tp / np.float32(true_count), [np.float32(2.0)]]).astype(np.float32)
+    levels = np.arange(num_points, dtype=np.float32) / np.float32(num_points - 1)
+    return float(np.mean([precisions[recalls >= r].max() for r in levels], dtype=np.float32))

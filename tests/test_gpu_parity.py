@@ -581,3 +581,53 @@ def test_roi_stream_kernels_vs_walk_kernels_random_shapes(det):
                         for i, h in enumerate(halves)], -1)
         tol = 2e-5 * max(float(gw.abs().max()), 1e-6)
         assert float((gs - gw).abs().max()) <= tol, (it, B, R, Hf, Wf)
+
+
+def test_average_precision_matching_and_metric(det, rng):
+    """utils/metrics.py:4-133: the batched matching kernel against the NumPy restatement (exact: IoU
+    is bit-identical, arg-max takes the first maximum), then the AP / mAP numbers (1e-6: identical fp32 arithmetic)."""
+    from oracle import reference_np as ref
+    B, G, M = 4, 100, 300
+    gt = np.zeros((B, G, 4), F)
+    pred = np.zeros((B, M, 4), F)
+    scores = np.zeros((B, M), F)
+    for b in range(B):
+        n = int(rng.integers(0 if b == 3 else 1, 20)) if b != 3 else 0   # image 3: no ground truth at all
+        xy, wh = rng.uniform(0, 0.7, (n, 2)), rng.uniform(0.05, 0.3, (n, 2))
+        gt[b, :n] = np.concatenate([xy, xy + wh], -1)
+        k = int(rng.integers(50, 250))                                  # the rest stays zero padded (score 0)
+        base = gt[b, rng.integers(0, max(n, 1), k)] if n else rng.uniform(0, 1, (k, 4))
+        pred[b, :k] = (base + rng.normal(0, 0.03, (k, 4))).astype(F)
+        pred[b, 5] = pred[b, 4]                                         # duplicate prediction: first maximum wins
+        scores[b, :k] = np.sort(rng.uniform(0.01, 1, k))[::-1]
+    ap = det.AveragePrecision(0.5)
+    ap.update_state(dev(gt[:2]), dev(pred[:2]), dev(scores[:2]))
+    ap.update_state(dev(gt[2:]), dev(pred[2:]), dev(scores[2:]))
+    tps, total = [], 0
+    for b in range(B):
+        tp, n = ref.ap_true_positives(gt[b], pred[b], 0.5)
+        tps.append(tp)
+        total += n
+    np.testing.assert_array_equal(host(torch.cat(ap._true_pos)), np.concatenate(tps))
+    assert int(ap.true_count) == total and ap.pos_count == B * M
+    np.testing.assert_allclose(float(ap.result()), ref.average_precision(np.concatenate(tps), scores.reshape(-1), total), rtol=1e-6)
+    # mAP over 3 classes == mean of per-class APs fed with the masked tensors
+    labels = np.zeros((B, G, 4), F)
+    cls = rng.integers(0, 3, (B, G))
+    valid = gt.sum(-1) != 0
+    labels[np.arange(B)[:, None], np.arange(G)[None, :], 1 + cls] = 1
+    labels[~valid] = 0
+    pcls = rng.integers(0, 3, (B, M)).astype(np.int32)
+    m = det.MeanAveragePrecision(3, 0.5)
+    m.update_state(dev(gt), dev(labels), dev(pred), dev(scores), torch.as_tensor(pcls).cuda())
+    want = []
+    for c in range(3):
+        tps, total = [], 0
+        sc = np.where(pcls == c, scores, 0).astype(F)
+        for b in range(B):
+            tp, n = ref.ap_true_positives(np.where((labels[b, :, 1 + c] == 1)[:, None], gt[b], 0),
+                                          np.where((pcls[b] == c)[:, None], pred[b], 0), 0.5)
+            tps.append(tp)
+            total += n
+        want.append(ref.average_precision(np.concatenate(tps), sc.reshape(-1), total))
+    np.testing.assert_allclose(float(m.result()), float(np.mean(want)), rtol=1e-5)

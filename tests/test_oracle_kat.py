@@ -419,3 +419,19 @@ def test_losses_known_answers():
     pb = np.array([[[[1.5, 1, 3, 1]], [[9, 9, 9, 9]], [[2, -2, 0, 1]], [[0, 0, 0, 3.5]]]], np.float32)
     assert abs(rnp.regression_loss(tb, pb) - ((0.125 + 0 + 1.5 + 0) / 4 + 0.125 / 4)) < 1e-6         # 0.40625 + 0.03125
     assert rnp.regression_loss(np.zeros((1, 2, 1, 4), np.float32), np.ones((1, 2, 1, 4), np.float32)) == 0.0
+
+
+def test_average_precision_known_answers():
+    """utils/metrics.py:4-84, hand-computed: two gt boxes, three predictions.  gt 0 is best matched by prediction 1
+    (IoU 0.81 > 0.5), gt 1 by prediction 2 (IoU 1/7 <= 0.5): TP = [0, 1, 0].  Sorted by score (0.9, 0.8, 0.1):
+    TP order [0, 1, 0] -> precision 0, 1/2, 1/3; recall 0, 1/2, 1/2.  11-point interpolation: recall levels 0..0.5 see
+    max precision 1/2, levels 0.6..1.0 only the sentinel 0 -> AP = 6 * 0.5 / 11."""
+    gt = np.array([[0, 0, 10, 10], [20, 20, 30, 30], [0, 0, 0, 0]], np.float32)      # last row: padding
+    pred = np.array([[50, 50, 60, 60], [1, 1, 10, 10], [25, 25, 35, 35]], np.float32)
+    tp, n = rnp.ap_true_positives(gt, pred, 0.5)
+    assert tp.tolist() == [0, 1, 0] and n == 2
+    ap = rnp.average_precision(tp, np.array([0.9, 0.8, 0.1], np.float32), n)
+    assert abs(ap - 6 * 0.5 / 11) < 1e-6
+    # a gt box that overlaps nothing selects prediction 0 (argmax of zeros) but IoU 0 is not > threshold
+    tp2, _ = rnp.ap_true_positives(np.array([[100, 100, 110, 110]], np.float32), pred, 0.0)
+    assert tp2.tolist() == [0, 0, 0]
