@@ -32,9 +32,10 @@ namespace {
 
 constexpr int kS = 14;                         // crop size = pooled_size * kernel_size
 constexpr int kP = 7;
-constexpr int kChunk = 512;                    // channels per CTA
+constexpr int kChunk = 256;                    // channels per CTA
 constexpr int kWarpCh = 64;                    // channels per warp: one float2 per lane
 constexpr int kWarps = kChunk / kWarpCh;
+static_assert(kWarps >= 2, "the prologue uses two warps (columns / rows)");
 constexpr int kThreads = kWarps * 32;
 constexpr int kPixBytes = kWarpCh * 4;         // one pixel in a warp's ring
 constexpr int kRingPix = 52;                   // pixels per warp ring: 8 warps x 52 x 256 B = 104 KB per CTA
@@ -279,7 +280,7 @@ __device__ __forceinline__ void crop_row(const u64 (&T)[kS], const u64 (&Bm)[kS]
 // kC = number of channels when known at compile time (1024: the reference's backbone; store offsets become immediates), 0 = any
 // kCodes: training forward, also writes the arg-max codes ([B,R,P,P,C/4] bytes: four 2-bit window positions per byte)
 template <int kC, bool kCodes>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 512 / kThreads)
     roi_pool_fwd_stream_kernel(const __grid_constant__ TensorMaps maps, const float* __restrict__ feat, int Hf, int Wf, int C_,
                                const float4* __restrict__ rois, int R, int nchunk, float* __restrict__ out,
                                unsigned char* __restrict__ codes) {
@@ -291,7 +292,12 @@ __global__ void __launch_bounds__(kThreads, 2)
     const int r = blockIdx.x / nchunk, ch0 = (blockIdx.x % nchunk) * kChunk, b = blockIdx.y;
     const unsigned full_base = smem_u32(&sh.full[0][0]);
 
-    // Prologue: warp 0 prepares the columns, warp 1 the rows (in parallel), warps 2-3 initialise the mbarriers.
+    // every warp initialises the mbarriers of its own ring
+    if (lane < kMaxDepth) {
+        mbar_init(full_base + (warp * kMaxDepth + lane) * 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // Prologue: warp 0 prepares the columns, warp 1 the rows (in parallel).
     if (tid < 32) {
         const float4 roi = rois[(size_t)b * R + r];  // x1,y1,x2,y2 (fast_rcnn_detector.py:157-158 reorders for TF)
         const Sample xs = sample_axis(roi.x, roi.z, Wf, lane);  // lanes 0..13 are the crop columns
@@ -365,9 +371,6 @@ __global__ void __launch_bounds__(kThreads, 2)
             sh.n_before = n_before;
             sh.n_after = kS - n_before - __popc(mv);
         }
-    } else if (tid < 64 + kWarps * kMaxDepth) {
-        mbar_init(full_base + (tid - 64) * 8, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (sh.wide) {  // rare (x-samples more than 51 columns apart): one bilinear gather per sample, same arithmetic
@@ -699,7 +702,7 @@ __device__ __forceinline__ void bwd_flush(BwdWalk& w, u64 (&G)[kS], const float 
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 512 / kThreads)
     roi_pool_bwd_stream_kernel(const __grid_constant__ BwdMaps maps, int Hf, int Wf, int C, const float4* __restrict__ rois, int R,
                                int nchunk, const float* __restrict__ dy, const unsigned char* __restrict__ codes,
                                float* __restrict__ dfeat) {
@@ -711,6 +714,10 @@ __global__ void __launch_bounds__(kThreads, 2)
     const unsigned dfull_base = smem_u32(&sh.dfull[0][0]);
     const unsigned all = 0xffffffffu;
 
+    if (lane < kBwdDySlots) {  // every warp initialises the mbarriers of its own dY ring
+        mbar_init(dfull_base + (warp * kBwdDySlots + lane) * 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     if (tid < 32) {  // warp 0: the columns
         const float4 roi = rois[(size_t)b * R + r];
         const Sample xs = sample_axis(roi.x, roi.z, Wf, lane);
@@ -775,9 +782,6 @@ __global__ void __launch_bounds__(kThreads, 2)
             sh.n_before = n_before;
             sh.n_after = kS - n_before - __popc(mv);
         }
-    } else if (tid < 64 + kWarps * kBwdDySlots) {
-        mbar_init(dfull_base + (tid - 64) * 8, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
@@ -1117,7 +1121,7 @@ __device__ __forceinline__ void persist_load_row(PWalk& w, PersistShared& sh, co
 }
 
 template <int kC, bool kCodes>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 512 / kThreads)
     roi_pool_fwd_persist_kernel(const __grid_constant__ TensorMaps maps, const float* __restrict__ feat, int Hf, int Wf, int C_,
                                 const float4* __restrict__ rois, int R, int nchunk, int n_items, float* __restrict__ out,
                                 unsigned char* __restrict__ codes, unsigned* __restrict__ counters) {
@@ -1395,7 +1399,8 @@ int get_bwd_maps(float* dfeat, long long pixels, const float* dy, const unsigned
 
 }  // namespace
 
-bool roi_pool_stream_supported(int C, int P, int k) { return C % kChunk == 0 && P == kP && k == 2; }
+// (512: the shapes this path is tuned and cross-checked for; narrower maps keep the bin-row walk)
+bool roi_pool_stream_supported(int C, int P, int k) { return C % 512 == 0 && C % kChunk == 0 && P == kP && k == 2; }
 
 int launch_roi_pool_fwd_stream(const float* feat, int B, int Hf, int Wf, int C, const float* rois, int R, float* out,
                                unsigned char* codes, cudaStream_t st) {
@@ -1446,7 +1451,8 @@ int launch_roi_pool_fwd_stream(const float* feat, int B, int Hf, int Wf, int C, 
         int sms = 0;
         FRCNN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         const int n_items = B * R * nchunk;
-        const int ctas = n_items < 2 * sms ? n_items : 2 * sms;
+        const int per_sm = 512 / kThreads;
+        const int ctas = n_items < per_sm * sms ? n_items : per_sm * sms;
         unsigned* ctr = counters[dev] + 2 * slot;
         if (codes) {
             if (C == 1024) roi_pool_fwd_persist_kernel<1024, true><<<ctas, kThreads, psmem, st>>>(*maps, feat, Hf, Wf, C, r4, R, nchunk, n_items, out, codes, ctr);
