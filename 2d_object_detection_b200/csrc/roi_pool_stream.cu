@@ -1,7 +1,7 @@
 // Row-streaming RoI pooling forward for the reference configuration (pooled_size 7, kernel_size 2: a 14 x 14
 // crop_and_resize max-pooled 2 x 2; models/detectors/fast_rcnn_detector.py:134-177).
 //
-// CTA = one RoI x 512 channels, 8 warps; a warp owns 64 channels (one float2 per lane; 128 registers, 2 CTAs per SM)
+// CTA = one RoI x 256 channels, 4 warps; a warp owns 64 channels (one float2 per lane; 128 registers, 4 CTAs per SM)
 // and runs its OWN copy pipeline -- after the prologue the warps never synchronise with each other.
 //   * Prologue (registers + shuffles; warp 0 the columns, warp 1 the rows, in parallel): the feature columns
 //     [cmin, cmax] under the 14 x-samples select one of eight TMA tensor maps (box = 64 channels x W pixels, W >= the
@@ -38,7 +38,7 @@ constexpr int kWarps = kChunk / kWarpCh;
 static_assert(kWarps >= 2, "the prologue uses two warps (columns / rows)");
 constexpr int kThreads = kWarps * 32;
 constexpr int kPixBytes = kWarpCh * 4;         // one pixel in a warp's ring
-constexpr int kRingPix = 52;                   // pixels per warp ring: 8 warps x 52 x 256 B = 104 KB per CTA
+constexpr int kRingPix = 52;                   // pixels per warp ring: 4 warps x 52 x 256 B = 52 KB per CTA, 208 KB per SM
 constexpr int kWarpRingBytes = kRingPix * kPixBytes;
 constexpr int kRingBytes = kWarps * kWarpRingBytes;
 constexpr int kMaxDepth = 8;
@@ -921,7 +921,7 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads)
 
 // ================================================================================================
 // Persistent variant of the forward walk.  The kernel above pays, per RoI, for a prologue every warp waits on and for
-// one exposed L2 -> shared-memory latency before the first row can be interpolated.  Here a CTA (8 warps, 512 channels)
+// one exposed L2 -> shared-memory latency before the first row can be interpolated.  Here a CTA (4 warps, 256 channels)
 // stays resident and fetches (RoI, channel chunk) items from a global counter; the tables of item n + 1 are computed by
 // one warp (rotating duty) while all warps work on item n, into a double-buffered "park" guarded by two mbarrier pairs;
 // and every warp's copy pipeline simply runs on into the next item: its ring has four fixed 13-pixel slots, a row of an
