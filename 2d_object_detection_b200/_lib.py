@@ -38,6 +38,8 @@ SIGNATURES = {
     "frcnn_postprocess_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "frcnn_postprocess": (_i, [_f, _f, _p, _i, _p, _p, _i, _i, _i, _f, _f, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p,
                                _sz, _p]),
+    "frcnn_postprocess_logits": (_i, [_f, _f, _p, _i, _p, _p, _p, _i, _i, _i, _f, _f, _i, _i, _i, _p, _p, _p, _p, _p, _p,
+                                      _p, _sz, _p]),
     "frcnn_decode_filter": (_i, [_f, _f, _p, _i, _p, _p, _i, _i, _i, _f, _p, _p, _p]),
     "frcnn_nms_workspace_bytes": (_sz, [_i, _i]),
     "frcnn_nms": (_i, [_p, _p, _i, _i, _f, _f, _i, _i, _p, _p, _p, _p, _sz, _p]),

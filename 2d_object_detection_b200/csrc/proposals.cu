@@ -19,12 +19,20 @@ namespace frcnn {
 // Stage 1: decode + to_relative + background drop + score threshold.
 // boxes_rel is class-major [B,nc,N,4] so each NMS segment is contiguous; keys are the order-preserving
 // score keys (0 = not a candidate).  Boxes stay UNCLIPPED here (trap T2).
+//
+// kLogits: `scores` holds the classification head's raw outputs after the reshape (rpn_detector.py:81-83,
+// fast_rcnn_detector.py:60-61) and the Softmax activation (rpn_detector.py:84) is computed here, so the
+// probabilities never round-trip through HBM before the threshold (second half):
+//   p_j = exp(l_j - max_k l_k) / sum_k exp(l_k - max_k l_k), sum left to right, IEEE division
+// (the form of TF's GPU kernel; Eigen's CPU kernel multiplies by the reciprocal of the sum instead: <= 1 ulp apart).
+// softmax_out (optional, [B,N,nc+1]) receives the probabilities the training losses need.
 // ------------------------------------------------------------------------------------------------
-template <bool kSingleClass>
+template <bool kSingleClass, bool kLogits>
 __global__ void __launch_bounds__(256)
     decode_filter_kernel(float img_h, float img_w, const float4* __restrict__ regions, int regions_batched,
                          const float* __restrict__ scores, const float4* __restrict__ deltas, int B, int N, int nc,
-                         float thr, float4* __restrict__ boxes_rel, uint32_t* __restrict__ keys) {
+                         float thr, float4* __restrict__ boxes_rel, uint32_t* __restrict__ keys,
+                         float* __restrict__ softmax_out) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t total = (int64_t)B * N * nc;
     if (i >= total) return;
@@ -45,7 +53,27 @@ __global__ void __launch_bounds__(256)
     const float4 rel = make_float4(fdiv(d.x, img_w), fdiv(d.y, img_h), fdiv(d.z, img_w), fdiv(d.w, img_h));  // :86-93
     float s;
     if (kSingleClass) {
-        s = __ldg(reinterpret_cast<const float2*>(scores) + bn).y;  // [bg, fg] pair, one 8-byte load
+        const float2 p = __ldg(reinterpret_cast<const float2*>(scores) + bn);  // [bg, fg] pair, one 8-byte load
+        if (kLogits) {
+            const float m = fmaxf(p.x, p.y);
+            const float e0 = expf(fsub(p.x, m)), e1 = expf(fsub(p.y, m));
+            const float sum = fadd(e0, e1);
+            s = fdiv(e1, sum);
+            if (softmax_out) reinterpret_cast<float2*>(softmax_out)[bn] = make_float2(fdiv(e0, sum), s);
+        } else {
+            s = p.y;
+        }
+    } else if (kLogits) {
+        const float* row = scores + bn * (nc + 1);
+        float m = __ldg(row);
+        for (int j = 1; j <= nc; ++j) m = fmaxf(m, __ldg(row + j));
+        float sum = 0.0f;
+        for (int j = 0; j <= nc; ++j) sum = fadd(sum, expf(fsub(__ldg(row + j), m)));
+        s = fdiv(expf(fsub(__ldg(row + 1 + c), m)), sum);
+        if (softmax_out) {
+            softmax_out[bn * (nc + 1) + 1 + c] = s;
+            if (c == 0) softmax_out[bn * (nc + 1)] = fdiv(expf(fsub(__ldg(row), m)), sum);
+        }
     } else {
         s = __ldg(scores + bn * (nc + 1) + 1 + c);  // post_processing.py:52 drop background column
     }
@@ -532,28 +560,38 @@ size_t frcnn_postprocess_workspace_bytes(int B, int N, int nc, int max_per_class
     return carve_post_ws(nullptr, B, N, nc, cap).bytes;
 }
 
-int frcnn_decode_filter(float img_h, float img_w, const float* regions, int regions_batched, const float* pred_scores,
-                        const float* pred_boxes, int B, int N, int nc, float score_threshold, float* boxes_rel,
-                        uint32_t* keys, frcnn_stream_t stream) {
+static int launch_decode_filter(float img_h, float img_w, const float* regions, int regions_batched,
+                                const float* pred_scores, int logits, float* softmax_out, const float* pred_boxes, int B,
+                                int N, int nc, float score_threshold, float* boxes_rel, uint32_t* keys,
+                                frcnn_stream_t stream) {
     FRCNN_REQUIRE(B > 0 && N >= 0 && nc > 0, FRCNN_EINVAL, "decode_filter: bad shape B=%d N=%d nc=%d", B, N, nc);
     FRCNN_REQUIRE(aligned16(regions) && aligned16(pred_boxes) && aligned16(boxes_rel) &&
-                      (reinterpret_cast<uintptr_t>(pred_scores) & 7u) == 0,
+                      (reinterpret_cast<uintptr_t>(pred_scores) & 7u) == 0 &&
+                      (reinterpret_cast<uintptr_t>(softmax_out) & 7u) == 0,
                   FRCNN_EINVAL, "decode_filter: pointers must be 16-byte aligned");
+    FRCNN_REQUIRE(logits || !softmax_out, FRCNN_EINVAL, "decode_filter: softmax_out needs logits input");
     const int64_t total = (int64_t)B * N * nc;
     if (total == 0) return 0;
     const unsigned grid = (unsigned)((total + 255) / 256);
-    if (nc == 1)
-        decode_filter_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(img_h, img_w, (const float4*)regions,
-                                                                        regions_batched, pred_scores,
-                                                                        (const float4*)pred_boxes, B, N, nc,
-                                                                        score_threshold, (float4*)boxes_rel, keys);
-    else
-        decode_filter_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(img_h, img_w, (const float4*)regions,
-                                                                         regions_batched, pred_scores,
-                                                                         (const float4*)pred_boxes, B, N, nc,
-                                                                         score_threshold, (float4*)boxes_rel, keys);
+#define FRCNN_DF(S, L)                                                                                                  \
+    decode_filter_kernel<S, L><<<grid, 256, 0, as_stream(stream)>>>(img_h, img_w, (const float4*)regions, regions_batched, \
+                                                                    pred_scores, (const float4*)pred_boxes, B, N, nc,  \
+                                                                    score_threshold, (float4*)boxes_rel, keys, softmax_out)
+    if (nc == 1) {
+        if (logits) FRCNN_DF(true, true); else FRCNN_DF(true, false);
+    } else {
+        if (logits) FRCNN_DF(false, true); else FRCNN_DF(false, false);
+    }
+#undef FRCNN_DF
     FRCNN_LAUNCH_CHECK("decode_filter_kernel");
     return 0;
+}
+
+int frcnn_decode_filter(float img_h, float img_w, const float* regions, int regions_batched, const float* pred_scores,
+                        const float* pred_boxes, int B, int N, int nc, float score_threshold, float* boxes_rel,
+                        uint32_t* keys, frcnn_stream_t stream) {
+    return launch_decode_filter(img_h, img_w, regions, regions_batched, pred_scores, 0, nullptr, pred_boxes, B, N, nc,
+                                score_threshold, boxes_rel, keys, stream);
 }
 
 size_t frcnn_nms_workspace_bytes(int segments, int N) {
@@ -580,11 +618,11 @@ int frcnn_nms(const float* boxes, const float* scores, int segments, int N, floa
                       exhausted, as_stream(stream));
 }
 
-int frcnn_postprocess(float img_h, float img_w, const float* regions, int regions_batched, const float* pred_scores,
-                      const float* pred_boxes, int B, int N, int nc, float score_threshold, float iou_threshold,
-                      int max_per_class, int max_total, int pre_nms_top_n, float* out_boxes, float* out_scores,
-                      int32_t* out_classes, int32_t* out_valid, int32_t* out_idx, int32_t* out_exhausted,
-                      void* workspace, size_t workspace_bytes, frcnn_stream_t stream) {
+static int postprocess_impl(float img_h, float img_w, const float* regions, int regions_batched, const float* pred_scores,
+                            int logits, float* softmax_out, const float* pred_boxes, int B, int N, int nc,
+                            float score_threshold, float iou_threshold, int max_per_class, int max_total, int pre_nms_top_n,
+                            float* out_boxes, float* out_scores, int32_t* out_classes, int32_t* out_valid, int32_t* out_idx,
+                            int32_t* out_exhausted, void* workspace, size_t workspace_bytes, frcnn_stream_t stream) {
     FRCNN_REQUIRE(B > 0 && N >= 0 && nc > 0 && max_per_class >= 0 && max_total > 0, FRCNN_EINVAL,
                   "postprocess: bad shape B=%d N=%d nc=%d per_class=%d total=%d", B, N, nc, max_per_class, max_total);
     FRCNN_REQUIRE(aligned16(out_boxes) && out_scores && out_classes && out_valid, FRCNN_EINVAL,
@@ -596,8 +634,8 @@ int frcnn_postprocess(float img_h, float img_w, const float* regions, int region
                   FRCNN_EWORKSPACE, "postprocess: workspace too small");
     cudaStream_t st = as_stream(stream);
     PostWs w = carve_post_ws(workspace, B, N, nc, cap);
-    int rc = frcnn_decode_filter(img_h, img_w, regions, regions_batched, pred_scores, pred_boxes, B, N, nc,
-                                 score_threshold, (float*)w.boxes_rel, w.keys, stream);
+    int rc = launch_decode_filter(img_h, img_w, regions, regions_batched, pred_scores, logits, softmax_out, pred_boxes, B,
+                                  N, nc, score_threshold, (float*)w.boxes_rel, w.keys, stream);
     if (rc) return rc;
     rc = launch_nms(w.boxes_rel, w.keys, B * nc, N, cap, pre_nms_top_n, iou_threshold, w.kept_idx, w.kept_count,
                     w.exhausted, st);
@@ -620,6 +658,26 @@ int frcnn_postprocess(float img_h, float img_w, const float* regions, int region
                                                           p2);
     FRCNN_LAUNCH_CHECK("finalize_kernel");
     return 0;
+}
+
+int frcnn_postprocess(float img_h, float img_w, const float* regions, int regions_batched, const float* pred_scores,
+                      const float* pred_boxes, int B, int N, int nc, float score_threshold, float iou_threshold,
+                      int max_per_class, int max_total, int pre_nms_top_n, float* out_boxes, float* out_scores,
+                      int32_t* out_classes, int32_t* out_valid, int32_t* out_idx, int32_t* out_exhausted,
+                      void* workspace, size_t workspace_bytes, frcnn_stream_t stream) {
+    return postprocess_impl(img_h, img_w, regions, regions_batched, pred_scores, 0, nullptr, pred_boxes, B, N, nc,
+                            score_threshold, iou_threshold, max_per_class, max_total, pre_nms_top_n, out_boxes, out_scores,
+                            out_classes, out_valid, out_idx, out_exhausted, workspace, workspace_bytes, stream);
+}
+
+int frcnn_postprocess_logits(float img_h, float img_w, const float* regions, int regions_batched, const float* pred_logits,
+                             float* softmax_out, const float* pred_boxes, int B, int N, int nc, float score_threshold,
+                             float iou_threshold, int max_per_class, int max_total, int pre_nms_top_n, float* out_boxes,
+                             float* out_scores, int32_t* out_classes, int32_t* out_valid, int32_t* out_idx,
+                             int32_t* out_exhausted, void* workspace, size_t workspace_bytes, frcnn_stream_t stream) {
+    return postprocess_impl(img_h, img_w, regions, regions_batched, pred_logits, 1, softmax_out, pred_boxes, B, N, nc,
+                            score_threshold, iou_threshold, max_per_class, max_total, pre_nms_top_n, out_boxes, out_scores,
+                            out_classes, out_valid, out_idx, out_exhausted, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -10,7 +10,8 @@ from .._tensor import as_device, check, lib, ptr, stream, workspace
 
 
 def postprocess_output(image_shape, regions, pred_scores, pred_boxes, score_threshold, iou_threshold,
-                       max_output_size_per_class, max_total_size, pre_nms_top_n=None, return_extra=False):
+                       max_output_size_per_class, max_total_size, pre_nms_top_n=None, return_extra=False,
+                       from_logits=False, return_softmax=False):
     """utils/post_processing.py:6-63.
 
     Args (as the reference): image_shape (H, W, _); regions [N,4] or [B,N,4] abs; pred_scores [B,N,nc+1];
@@ -21,6 +22,12 @@ def postprocess_output(image_shape, regions, pred_scores, pred_boxes, score_thre
     "num_valid_detections" [B] int32}, zero padded; with ``return_extra`` also "kept_indices" [B,R] int32
     (-1 padded) and "exhausted" [B] int32 (1 = pre_nms_top_n cut the list before the per-class cap).
     Outputs carry no gradient (the reference wraps them in tf.stop_gradient, :57-63).
+
+    ``from_logits`` (extension): ``pred_scores`` holds the classification head's reshaped pre-activation outputs and
+    the Softmax of models/detectors/rpn_detector.py:84 is fused into the decode kernel (frcnn_postprocess_logits);
+    with ``return_softmax`` the probabilities come back as "softmax_scores" [B,N,nc+1] (what the detector returns as
+    ``pred_scores`` and the losses read).  The selection is bit-identical to calling this function on those
+    probabilities.
     """
     reg, sc, pb = as_device(regions), as_device(pred_scores), as_device(pred_boxes)
     if pb.dim() != 4 or pb.shape[-1] != 4:
@@ -43,13 +50,25 @@ def postprocess_output(image_shape, regions, pred_scores, pred_boxes, score_thre
     L = lib()
     ws_bytes = L.frcnn_postprocess_workspace_bytes(B, N, nc, per_class, R)
     ws = workspace(ws_bytes)
-    check(L.frcnn_postprocess(float(image_shape[0]), float(image_shape[1]), ptr(reg), int(batched), ptr(sc), ptr(pb),
-                              B, N, nc, float(score_threshold), float(iou_threshold), per_class, R,
-                              int(pre_nms_top_n or 0), ptr(out_boxes), ptr(out_scores), ptr(out_classes),
-                              ptr(out_valid), ptr(out_idx), ptr(out_exh), ptr(ws), ws_bytes, stream()),
-          "postprocess_output")
+    if return_softmax and not from_logits:
+        raise ValueError("return_softmax needs from_logits=True")
+    probs = torch.empty_like(sc) if return_softmax else None
+    if from_logits:
+        check(L.frcnn_postprocess_logits(float(image_shape[0]), float(image_shape[1]), ptr(reg), int(batched), ptr(sc),
+                                         ptr(probs), ptr(pb), B, N, nc, float(score_threshold), float(iou_threshold),
+                                         per_class, R, int(pre_nms_top_n or 0), ptr(out_boxes), ptr(out_scores),
+                                         ptr(out_classes), ptr(out_valid), ptr(out_idx), ptr(out_exh), ptr(ws),
+                                         ws_bytes, stream()), "postprocess_output")
+    else:
+        check(L.frcnn_postprocess(float(image_shape[0]), float(image_shape[1]), ptr(reg), int(batched), ptr(sc),
+                                  ptr(pb), B, N, nc, float(score_threshold), float(iou_threshold), per_class, R,
+                                  int(pre_nms_top_n or 0), ptr(out_boxes), ptr(out_scores), ptr(out_classes),
+                                  ptr(out_valid), ptr(out_idx), ptr(out_exh), ptr(ws), ws_bytes, stream()),
+              "postprocess_output")
     out = {"pred_boxes": out_boxes, "pred_scores": out_scores, "pred_classes": out_classes,
            "num_valid_detections": out_valid}
+    if return_softmax:
+        out["softmax_scores"] = probs
     if return_extra:
         out["kept_indices"] = out_idx
         out["exhausted"] = out_exh

@@ -111,6 +111,19 @@ FRCNN_API int frcnn_postprocess(float image_height, float image_width, const flo
                       float* out_scores, int32_t* out_classes, int32_t* out_valid, int32_t* out_idx,
                       int32_t* out_exhausted, void* workspace, size_t workspace_bytes, frcnn_stream_t stream);
 
+/* The same with the classification head's Softmax activation fused in (models/detectors/rpn_detector.py:81-84:
+ * 1x1 conv -> Reshape((-1, 2)) -> Softmax; fast_rcnn_detector.py:60-61 likewise): pred_logits [B,N,nc+1] are the
+ * reshaped pre-activation outputs, p_j = exp(l_j - max) / sum_k exp(l_k - max) (sum left to right, IEEE division)
+ * is computed in the decode kernel, so the probabilities are thresholded without a round trip through memory.
+ * softmax_out [B,N,nc+1] (nullable) receives the probabilities (the "pred_scores" the detector returns and the
+ * losses read).  Selection is bit-identical to frcnn_postprocess called on softmax_out. */
+FRCNN_API int frcnn_postprocess_logits(float image_height, float image_width, const float* regions, int regions_batched,
+                             const float* pred_logits, float* softmax_out, const float* pred_boxes, int B, int N, int nc,
+                             float score_threshold, float iou_threshold, int max_per_class, int max_total,
+                             int pre_nms_top_n, float* out_boxes, float* out_scores, int32_t* out_classes,
+                             int32_t* out_valid, int32_t* out_idx, int32_t* out_exhausted, void* workspace,
+                             size_t workspace_bytes, frcnn_stream_t stream);
+
 /* Stage 1 of the above (exposed for stage-level parity and profiling): fused decode + to_relative
  * + background-column drop + score threshold.  boxes_rel [B,nc,N,4] (class-major, unclipped: trap T2),
  * keys [B,nc,N] uint32 = order-preserving score key, 0 for score <= threshold / NaN. */

@@ -286,6 +286,19 @@ def generate_targets(gt_labels, gt_boxes, regions, image_shape, foreground_iou_i
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# Classification-head epilogue, models/detectors/rpn_detector.py:81-84 (1x1 conv -> Reshape((-1, 2)) -> Softmax) and
+# fast_rcnn_detector.py:60-61 (second half).  tf.keras.layers.Softmax over the last axis in the form of
+# TF's GPU kernel: exp(l - max) / sum(exp(l - max)), every operation rounded to float32, sum left to right.
+def softmax(logits):
+    l = np.asarray(logits, np.float32)
+    e = np.exp(l - l.max(-1, keepdims=True)).astype(np.float32)
+    tot = np.zeros(l.shape[:-1], np.float32)
+    for j in range(l.shape[-1]):
+        tot = (tot + e[..., j]).astype(np.float32)
+    return (e / tot[..., None]).astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # utils/losses.py:4-43.  tf.keras.losses.CategoricalCrossentropy() on probabilities and
 # tf.keras.losses.Huber(reduction=NONE) with the reference's row filter; float32 element arithmetic, float64 only for
 # the final reductions (Eigen's reduction order is unspecified: compare within 1e-5).

@@ -61,6 +61,15 @@ def main():
                {"exhausted_images": int(out["exhausted"].sum()), "num_valid_min": int(out["num_valid_detections"].min())})
         ms = timeit(lambda: det.postprocess_output(w.image_shape, anchors, scores, deltas, **kw, pre_nms_top_n=None), flush=flush)
         report("postprocess_output, no pre-NMS cap (reference behaviour)", wname, ms, B * (44 * N + 4 * N + 40 * N + 24 * R))
+        # head epilogue (rpn_detector.py:81-84): softmax fused into the decode kernel vs a separate softmax launch
+        logits = torch.randn((B, N, 2), device=dev) * 1.5
+        ms = timeit(lambda: det.postprocess_output(w.image_shape, anchors, logits, deltas, **kw, pre_nms_top_n=w.pre_nms_top_n,
+                                                   from_logits=True, return_softmax=True), flush=flush)
+        report("postprocess_output from logits (softmax fused, probabilities written)", wname, ms, B * (44 * N + 8 * N + 4 * N))
+        ms = timeit(lambda: det.postprocess_output(w.image_shape, anchors, torch.softmax(logits, -1), deltas, **kw,
+                                                   pre_nms_top_n=w.pre_nms_top_n), flush=flush)
+        report("torch.softmax + postprocess_output (unfused)", wname, ms, B * (44 * N + 16 * N + 4 * N))
+        del logits
         rois = out["pred_boxes"]
         ms = timeit(lambda: det.roi_pool_forward(feat, rois, 7, 2), flush=flush)
         report("roi_pool_forward", wname, ms, 4 * C * (Hf * Wf + 49 * R) * B)

@@ -202,6 +202,49 @@ def test_postprocess_rcnn_form_multiclass(det, orc, syn, rng):
     assert (host(out["pred_boxes"])[0, nv[0]:] == 0).all() and (host(out["pred_scores"])[0, nv[0]:] == 0).all()
 
 
+def _check_fused_softmax(det, orc, image_shape, regions, logits, deltas, kw):
+    """frcnn_postprocess_logits: probabilities within a few ulp of the oracle's softmax, selection bit-identical to the
+    unfused call on those probabilities, and both equal to the oracle's postprocess_output on them."""
+    from oracle import reference_np as ref
+    fused = det.postprocess_output(image_shape, dev(regions), dev(logits), dev(deltas), **kw, return_extra=True,
+                                   from_logits=True, return_softmax=True)
+    probs = fused["softmax_scores"]
+    np.testing.assert_allclose(host(probs), ref.softmax(logits), rtol=2e-6, atol=1e-30)  # expf: <= 2 ulp, then one division
+    plain = det.postprocess_output(image_shape, dev(regions), probs, dev(deltas), **kw, return_extra=True)
+    for k in ("pred_boxes", "pred_scores", "pred_classes", "num_valid_detections", "kept_indices", "exhausted"):
+        assert torch.equal(fused[k], plain[k]), k
+    _check_post(det, orc, image_shape, regions, host(probs), deltas, kw)
+    nosm = det.postprocess_output(image_shape, dev(regions), dev(logits), dev(deltas), **kw, return_extra=True, from_logits=True)
+    assert "softmax_scores" not in nosm and torch.equal(nosm["kept_indices"], fused["kept_indices"])
+    return fused
+
+
+def test_postprocess_from_logits_rpn_head_epilogue(det, orc, syn, rng):
+    # rpn_detector.py:81-84: the cls head's reshaped outputs [B, N, 2] -> Softmax, fused into the decode kernel
+    w, anchors, _, deltas, _ = _decoded(orc, syn, "kitti_b8", 4, 77)
+    logits = rng.normal(0, 1.5, (4, w.num_anchors, 2)).astype(F)
+    logits[0, :5] = [[90.0, -90.0], [-90.0, 90.0], [0.0, 0.0], [np.inf, 0.0], [np.nan, 1.0]]  # saturated, tie, inf, NaN rows
+    with np.errstate(invalid="ignore"):
+        out = _check_fused_softmax(det, orc, w.image_shape, anchors, logits, deltas, w.nms_kwargs())
+    p = host(out["softmax_scores"])
+    np.testing.assert_array_equal(p[0, :3], F([[1, 0], [0, 1], [0.5, 0.5]]))
+    assert np.isnan(p[0, 3:5]).all() and not np.isin(host(out["kept_indices"])[0], [3, 4]).any()  # NaN never a candidate
+    assert (host(out["num_valid_detections"]) == 300).all()
+    with pytest.raises(ValueError):
+        det.postprocess_output(w.image_shape, dev(anchors), dev(logits), dev(deltas), **w.nms_kwargs(), return_softmax=True)
+
+
+def test_postprocess_from_logits_multiclass(det, orc, syn, rng):
+    # fast_rcnn_detector.py:60-61 Dense -> Softmax over num_classes + 1
+    B, R, nc = 3, 300, 7
+    rois = syn.random_rois(rng, B, R) * F([1242, 375, 1242, 375])
+    logits = rng.normal(0, 1.5, (B, R, nc + 1)).astype(F)
+    dl = rng.normal(0, 0.1, (B, R, nc, 4)).astype(F)
+    for kw in (dict(score_threshold=0.0, iou_threshold=0.6, max_output_size_per_class=100, max_total_size=300),
+               dict(score_threshold=0.3, iou_threshold=0.5, max_output_size_per_class=10, max_total_size=300)):
+        _check_fused_softmax(det, orc, (375, 1242, 3), rois, logits, dl, kw)
+
+
 def test_postprocess_small_and_empty(det, orc, syn, rng):
     anchors = orc.generate_anchors((3, 4), [0.5, 1.0], [1.0], [64, 64])
     scores, deltas = syn.rpn_head_outputs(rng, 2, anchors.shape[0])

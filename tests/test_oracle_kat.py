@@ -435,3 +435,18 @@ def test_average_precision_known_answers():
     # a gt box that overlaps nothing selects prediction 0 (argmax of zeros) but IoU 0 is not > threshold
     tp2, _ = rnp.ap_true_positives(np.array([[100, 100, 110, 110]], np.float32), pred, 0.0)
     assert tp2.tolist() == [0, 0, 0]
+
+
+def test_softmax_known_answers():
+    """rpn_detector.py:84 Softmax over the (background, object) pair; stable for large logits."""
+    from oracle import reference_np as ref
+    np.testing.assert_array_equal(ref.softmax(np.zeros((3, 2), np.float32)), np.full((3, 2), 0.5, np.float32))
+    np.testing.assert_allclose(ref.softmax(np.float32([[0.0, np.log(3.0)]])), [[0.25, 0.75]], rtol=1e-6)
+    np.testing.assert_array_equal(ref.softmax(np.float32([[1000.0, 0.0], [-1000.0, 0.0]])), np.float32([[1, 0], [0, 1]]))
+    x = np.random.default_rng(3).normal(0, 3, (50, 8)).astype(np.float32)
+    p = ref.softmax(x)
+    assert p.dtype == np.float32
+    np.testing.assert_allclose(p.sum(-1), 1.0, atol=1e-6)
+    e = np.exp(x.astype(np.float64))
+    np.testing.assert_allclose(p, e / e.sum(-1, keepdims=True), rtol=1e-5)
+    np.testing.assert_array_equal(p.argmax(-1), x.argmax(-1))
