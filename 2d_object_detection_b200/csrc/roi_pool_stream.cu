@@ -614,19 +614,19 @@ __device__ __forceinline__ void bwd_crop_row(u64 (&G0)[kS], u64 (&G1)[kS], bool 
     const float wt = fsub(1.0f, yl);
     const float w0f = g0_top ? wt : yl, w1f = g0_top ? yl : wt;
     const u64 w0 = pack2(w0f, w0f), w1 = pack2(w1f, w1f);
-    // window position = 2 * (crop row in the bin) + (crop column in the bin).  After the flip a clear high bit means "this
-    // crop row holds the maximum"; the low bit says which of its two columns.  Single-bit tests compile to one
-    // predicate-producing LOP3 (or a shared R2P) each: no shift / mask / compare per sample.
-    const unsigned cwr = second ? (cw ^ 0x0AAAAAAAu) : cw;
+    // window position = 2 * (crop row in the bin) + (crop column in the bin).  c0 / c1 hold the codes XOR the position of
+    // this crop row's first / second column, so "this sample won" is "its two code bits are clear": one predicate-producing
+    // LOP3 and one FSEL per sample and channel (no shift / compare).
+    const unsigned c0 = second ? (cw ^ 0x0AAAAAAAu) : cw;
+    const unsigned c1 = c0 ^ 0x05555555u;
 #pragma unroll
     for (int j = 0; j < kP; ++j) {
         u64 dyv;
         asm volatile("ld.shared.b64 %0, [%1];" : "=l"(dyv) : "r"(dy_addr + j * kPixBytes));
         const float2 d = unpack2(dyv);
-        const bool rx = (cwr & (2u << (4 * j))) == 0u, ry = (cwr & (8u << (4 * j))) == 0u;
-        const bool lx = (cwr & (1u << (4 * j))) != 0u, ly = (cwr & (4u << (4 * j))) != 0u;
-        const float mx = rx ? d.x : 0.0f, my = ry ? d.y : 0.0f;
-        const u64 g0 = pack2(lx ? 0.0f : mx, ly ? 0.0f : my), g1 = pack2(lx ? mx : 0.0f, ly ? my : 0.0f);
+        const unsigned mx = 3u << (4 * j), my = 12u << (4 * j);
+        const u64 g0 = pack2((c0 & mx) == 0u ? d.x : 0.0f, (c0 & my) == 0u ? d.y : 0.0f);
+        const u64 g1 = pack2((c1 & mx) == 0u ? d.x : 0.0f, (c1 & my) == 0u ? d.y : 0.0f);
         G0[2 * j] = fma2(g0, w0, G0[2 * j]);
         G1[2 * j] = fma2(g0, w1, G1[2 * j]);
         G0[2 * j + 1] = fma2(g1, w0, G0[2 * j + 1]);
