@@ -246,11 +246,31 @@ __device__ __forceinline__ void take_if_greater(float& m, unsigned& cw, float v,
     }
 }
 
+// Arg-max tracking of the streaming walk: instead of rewriting a 2-bit position per candidate, every candidate after the
+// first only records "I beat the running maximum" in a flag bit (one predicated OR) and the maximum itself is a plain
+// FMNMX.  The last candidate that won is the first maximum in row-major window order (strict >: trap T8), so the 2-bit
+// code is rebuilt from the three flags with word-wide logic once per bin-row (codes_from_flags).
+//   word a: bit 4j + 2c     window position 1 won,   bit 4j + 2c + 1   position 2 won      (c = channel lane 0 / 1)
+//   word b: bit 4j + 2c     window position 3 won
+__device__ __forceinline__ void flag_if_greater(float& m, unsigned& word, float v, unsigned bit) {
+#ifdef FRCNN_FLAG_IF
+    if (v > m) word |= bit;
+#else
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(word) : "f"(v), "f"(m), "r"(bit));
+#endif
+    m = fmaxf(m, v);
+}
+__device__ __forceinline__ unsigned codes_from_flags(unsigned a, unsigned b) {
+    const unsigned won2 = (a >> 1) & 0x05555555u;                 // position 2 flags moved to the even bits
+    const unsigned lo = b | (a & 0x05555555u & ~won2);            // low code bit: position 3, or position 1 not beaten by 2
+    return lo | ((won2 | b) << 1);                                // high code bit: position 2 or 3
+}
+
 // Fold one finished crop row (top / bottom feature rows T / Bm, weight yl) into the 7 running bin maxima.  kFirst: first
 // crop row of the bin-row.  kCodes: also track which of the four window samples holds the maximum (training forward).
 template <bool kFirst, bool kCodes>
 __device__ __forceinline__ void crop_row(const u64 (&T)[kS], const u64 (&Bm)[kS], float yl, u64 one, float2 (&M)[kP],
-                                         unsigned& cw) {
+                                         unsigned& ca, unsigned& cb) {
     const u64 ww = pack2(yl, yl);
 #pragma unroll
     for (int j = 0; j < kP; ++j) {
@@ -258,14 +278,14 @@ __device__ __forceinline__ void crop_row(const u64 (&T)[kS], const u64 (&Bm)[kS]
         const float2 v1 = unpack2(lerp2(T[2 * j + 1], Bm[2 * j + 1], ww, one));
         if (kCodes) {
             if (kFirst) {
-                M[j] = v0;  // window position 0; cw was cleared for this bin-row
-                take_if_greater(M[j].x, cw, v1.x, 1u, 4 * j);
-                take_if_greater(M[j].y, cw, v1.y, 1u, 4 * j + 2);
+                M[j] = v0;  // window position 0; the flags were cleared for this bin-row
+                flag_if_greater(M[j].x, ca, v1.x, 1u << (4 * j));
+                flag_if_greater(M[j].y, ca, v1.y, 4u << (4 * j));
             } else {
-                take_if_greater(M[j].x, cw, v0.x, 2u, 4 * j);
-                take_if_greater(M[j].y, cw, v0.y, 2u, 4 * j + 2);
-                take_if_greater(M[j].x, cw, v1.x, 3u, 4 * j);
-                take_if_greater(M[j].y, cw, v1.y, 3u, 4 * j + 2);
+                flag_if_greater(M[j].x, ca, v0.x, 2u << (4 * j));
+                flag_if_greater(M[j].y, ca, v0.y, 8u << (4 * j));
+                flag_if_greater(M[j].x, cb, v1.x, 1u << (4 * j));
+                flag_if_greater(M[j].y, cb, v1.y, 4u << (4 * j));
             }
         } else if (kFirst) {
             M[j].x = fmaxf(v0.x, v1.x);
@@ -456,38 +476,39 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads)
     const int bin_stride = C / 2;  // float2 per bin
     int sy = 0;
     float yl_next = sh.ylerp[0];  // the y weight of the next crop row, loaded one crop row ahead
-    unsigned cw = 0u;  // kCodes: the 2-bit window positions of this lane's two channels for the 7 bins of the bin-row
+    unsigned ca = 0u, cb = 0u;  // kCodes: "candidate beat the running maximum" flags of the bin-row (see flag_if_greater)
     unsigned char* cptr = kCodes ? codes + ((size_t)b * R + r) * (kP * kP) * (C / 4) + (ch0 + tid * 2) / 4 : nullptr;
     // One finished crop row: fold it into the bin maxima; after the second row of a bin-row store the 7 bins.
     auto emit = [&](const u64 (&T)[kS], const u64 (&Bm)[kS], bool outside) {
         const float yl = yl_next;
         yl_next = sh.ylerp[min(sy + 1, kS - 1)];
         if (!(sy & 1)) {
-            cw = 0u;
+            ca = cb = 0u;
             if (outside) {  // crop row outside the map: extrapolation value 0 takes part in the max
 #pragma unroll
                 for (int j = 0; j < kP; ++j) M[j] = make_float2(0.0f, 0.0f);
             } else {
-                crop_row<true, kCodes>(T, Bm, yl, w.one, M, cw);
+                crop_row<true, kCodes>(T, Bm, yl, w.one, M, ca, cb);
             }
         } else {
             if (outside) {
 #pragma unroll
                 for (int j = 0; j < kP; ++j) {
                     if (kCodes) {  // window positions 2 and 3 are both 0: position 2 wins if 0 beats the first row
-                        take_if_greater(M[j].x, cw, 0.0f, 2u, 4 * j);
-                        take_if_greater(M[j].y, cw, 0.0f, 2u, 4 * j + 2);
+                        flag_if_greater(M[j].x, ca, 0.0f, 2u << (4 * j));
+                        flag_if_greater(M[j].y, ca, 0.0f, 8u << (4 * j));
                     } else {
                         M[j] = make_float2(fmaxf(M[j].x, 0.0f), fmaxf(M[j].y, 0.0f));
                     }
                 }
             } else {
-                crop_row<false, kCodes>(T, Bm, yl, w.one, M, cw);
+                crop_row<false, kCodes>(T, Bm, yl, w.one, M, ca, cb);
             }
 #pragma unroll
             for (int j = 0; j < kP; ++j) __stcs(optr + j * bin_stride, M[j]);
             optr += kP * bin_stride;
             if (kCodes) {  // a byte holds four channels = this lane's nibble and its odd neighbour's
+                const unsigned cw = codes_from_flags(ca, cb);
                 const unsigned pw = __shfl_xor_sync(0xffffffffu, cw, 1);
                 if (!(tid & 1)) {
 #pragma unroll
@@ -1220,34 +1241,35 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads)
             u64 prog = ((u64)__reduce_or_sync(all, pk.prog_hi) << 32) | __reduce_or_sync(all, pk.prog_lo);
             const int n_before = pk.n_before, n_after = pk.n_after;
             int sy = 0;
-            unsigned cw = 0u;
+            unsigned ca = 0u, cb = 0u;
             auto emit = [&](const u64 (&T)[kS], const u64 (&Bm)[kS], bool outside) {
                 if (!(sy & 1)) {
-                    cw = 0u;
+                    ca = cb = 0u;
                     if (outside) {
 #pragma unroll
                         for (int j = 0; j < kP; ++j) M[j] = make_float2(0.0f, 0.0f);
                     } else {
-                        crop_row<true, kCodes>(T, Bm, pk.ylerp[sy], one, M, cw);
+                        crop_row<true, kCodes>(T, Bm, pk.ylerp[sy], one, M, ca, cb);
                     }
                 } else {
                     if (outside) {
 #pragma unroll
                         for (int j = 0; j < kP; ++j) {
                             if (kCodes) {
-                                take_if_greater(M[j].x, cw, 0.0f, 2u, 4 * j);
-                                take_if_greater(M[j].y, cw, 0.0f, 2u, 4 * j + 2);
+                                flag_if_greater(M[j].x, ca, 0.0f, 2u << (4 * j));
+                                flag_if_greater(M[j].y, ca, 0.0f, 8u << (4 * j));
                             } else {
                                 M[j] = make_float2(fmaxf(M[j].x, 0.0f), fmaxf(M[j].y, 0.0f));
                             }
                         }
                     } else {
-                        crop_row<false, kCodes>(T, Bm, pk.ylerp[sy], one, M, cw);
+                        crop_row<false, kCodes>(T, Bm, pk.ylerp[sy], one, M, ca, cb);
                     }
 #pragma unroll
                     for (int j = 0; j < kP; ++j) __stcs(optr + j * bin_stride, M[j]);
                     optr += kP * bin_stride;
                     if (kCodes) {
+                        const unsigned cw = codes_from_flags(ca, cb);
                         const unsigned pw = __shfl_xor_sync(all, cw, 1);
                         if (!(lane & 1)) {
 #pragma unroll
