@@ -35,9 +35,20 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
+def _defines() -> str:
+    return " ".join(sorted(os.environ.get("FRCNN_DEFINES", "").split()))
+
+
 def is_stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
+    try:  # a library built with other -D switches (debug / experiment builds) is stale
+        with open(LIB_PATH + ".defines") as f:
+            if f.read().strip() != _defines():
+                return True
+    except OSError:
+        if _defines():
+            return True
     t = os.path.getmtime(LIB_PATH)
     deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))
     return any(os.path.getmtime(d) > t for d in deps)
@@ -58,6 +69,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(proc.stdout + proc.stderr)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stderr[-4000:])
+    with open(LIB_PATH + ".defines", "w") as f:
+        f.write(_defines() + "\n")
     return LIB_PATH
 
 
