@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Generate tests/golden/reference_exec.npz by EXECUTING THE REFERENCE'S OWN PYTHON SOURCE on small seeded inputs.
 
-STATUS: NOT YET RUN.  Importing and running modules from the reference tree needs a human's authorisation in the build
-environment (it is untrusted public content); this script is the prepared recipe.  tests/test_reference_golden.py skips
+STATUS: NOT YET RUN (attempted in rounds 1 and 2; the build sandbox's security classifier refuses to execute modules from
+the external reference tree without a human's authorisation -- DESIGN.md section 2 quotes the refusal).  This script is
+the prepared recipe for a maintainer who may run it.  tests/test_reference_golden.py skips
 until reference_exec.npz exists.
 
 The reference (TensorFlow 2) cannot run as is in the build container (no TensorFlow, no network).  Its hot-path modules,
