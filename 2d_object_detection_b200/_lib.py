@@ -51,10 +51,13 @@ SIGNATURES = {
     "frcnn_generate_targets_workspace_bytes": (_sz, [_i, _i]),
     "frcnn_generate_targets": (_i, [_p, _p, _i, _i, _i, _p, _i, _i, _f, _f, _f, _f, _f, _f, _p, _p, _p, _p, _p, _sz,
                                     _p]),
+    "frcnn_generate_targets_objectness": (_i, [_p, _p, _i, _i, _i, _p, _i, _i, _f, _f, _f, _f, _f, _f, _p, _p, _p, _p, _p,
+                                               _sz, _p]),
+    "frcnn_objectness_labels": (_i, [_p, _i64, _i, _p, _p]),
     "frcnn_ap_match": (_i, [_p, _i, _i, _p, _i, _f, _p, _p, _p]),
     "frcnn_sampled_losses": (_i, [_p, _p, _i64, _i, _p, _p, _i64, _f, _f, _p, _p, _p, _p]),
     "frcnn_sample_indices_workspace_bytes": (_sz, [_i, _i]),
-    "frcnn_sample_and_gather": (_i, [_p, _i, _i, _i, _i, _f, C.c_uint64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "frcnn_sample_and_gather": (_i, [_p, _i, _i, _i, _i, C.c_double, C.c_uint64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "frcnn_pipeline_create": (_i, [C.POINTER(_p), _i, _i, _i, _i, _i, _i, _i, _i]),
     "frcnn_pipeline_destroy": (None, [_p]),
     "frcnn_pipeline_run": (_i, [_p, _f, _f, _p, _p, _p, _p, _f, _f, _i, _p, _p, _p, _p]),

@@ -36,6 +36,21 @@ static inline cudaStream_t as_stream(frcnn_stream_t s) { return reinterpret_cast
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Raise a kernel's dynamic shared-memory limit.  The attribute is per function AND per device, so the high-water mark is
+// kept per device (a host thread may drive several GPUs); kSite gives every call site its own table.
+template <int kSite>
+static inline cudaError_t ensure_dynamic_smem(const void* func, size_t bytes) {
+    static thread_local size_t configured[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const bool cached = dev >= 0 && dev < 64;
+    if (cached && bytes <= configured[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess && cached) configured[dev] = bytes;
+    return e;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Exactly-rounded fp32 helpers.  The library is compiled with -fmad=false, and the parity-critical
 // expressions additionally use the _rn intrinsics so that no later flag change can contract them.

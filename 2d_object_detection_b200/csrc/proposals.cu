@@ -537,11 +537,7 @@ static int launch_nms(const float4* boxes, const uint32_t* keys, int segments, i
     FRCNN_REQUIRE(cap <= 4096, FRCNN_ELIMIT, "nms: min(max_output, N) = %d exceeds the 4096 limit", cap);
     FRCNN_REQUIRE(N < (1 << 22), FRCNN_ELIMIT, "nms: N = %d exceeds the 2^22 limit", N);
     const size_t smem = nms_smem_bytes(cap);
-    static thread_local size_t configured = 0;
-    if (smem > configured) {
-        FRCNN_CUDA(cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    FRCNN_CUDA(ensure_dynamic_smem<0>((const void*)nms_select_kernel, smem));
     nms_select_kernel<<<segments, kNmsThreads, smem, st>>>(boxes, keys, N, cap, top_n, iou_thr, kept_idx, kept_count,
                                                            exhausted);
     FRCNN_LAUNCH_CHECK("nms_select_kernel");
@@ -646,11 +642,7 @@ static int postprocess_impl(float img_h, float img_w, const float* regions, int 
         p2 = 32;
         while (p2 < nc * cap) p2 <<= 1;
         smem = sizeof(unsigned long long) * (size_t)p2;
-        static thread_local size_t configured = 0;
-        if (smem > 48 * 1024 && smem > configured) {
-            FRCNN_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
-        }
+        if (smem > 48 * 1024) FRCNN_CUDA(ensure_dynamic_smem<1>((const void*)finalize_kernel, smem));
     }
     finalize_kernel<<<B, nc > 1 ? 1024 : 256, smem, st>>>(w.boxes_rel, w.keys, N, nc, cap > 0 ? cap : 1, max_total,
                                                           w.kept_idx, w.kept_count, w.exhausted, (float4*)out_boxes,

@@ -7,11 +7,18 @@
 // owns one float4 of channels and walks the bins of one RoI, so every global access is a coalesced
 // 128-bit load/store.  Arithmetic follows the TF CPU kernel operation by operation with explicit _rn
 // intrinsics: the forward result is bit-identical to the CPU oracle.
-#include <stdlib.h>
-
 #include "roi_axis.cuh"
 
 namespace frcnn {
+
+// Compile-time A/B switch (FRCNN_DEFINES=FRCNN_AB_BINROW_WALK): route the reference shape to the older bin-row walk
+// kernels instead of the row-streaming ones.  Forward codes and backward always switch together.  Never set in the
+// shipped build: one path per shape, no run-time dispatch on the environment.
+#ifdef FRCNN_AB_BINROW_WALK
+constexpr bool kForceBinRowWalk = true;
+#else
+constexpr bool kForceBinRowWalk = false;
+#endif
 
 // ---- tiny vector abstraction: float4 (C % 4 == 0) or float -------------------------------------
 __device__ __forceinline__ float4 vload(const float4* p) { return __ldg(p); }
@@ -771,8 +778,7 @@ int frcnn_roi_pool_forward(const float* feat, int B, int Hf, int Wf, int C, cons
     FRCNN_REQUIRE(B <= 65535, FRCNN_ELIMIT, "roi_pool_forward: B > 65535");
     if (R == 0) return 0;
     const dim3 grid(R, B);
-    static const bool force_walk = getenv("FRCNN_FWD_WALK") != nullptr;  // A/B switch for benchmarking the older bin-row walk
-    if (roi_pool_stream_supported(C, P, k) && !force_walk)
+    if (roi_pool_stream_supported(C, P, k) && !kForceBinRowWalk)
         return launch_roi_pool_fwd_stream(feat, B, Hf, Wf, C, rois, R, out, nullptr, as_stream(stream));
     if (C % 4 == 0 && k == 2 && (int64_t)Hf * Wf * (C / 4) < (1ll << 31)) {
         const int cv = C / 4;
@@ -840,8 +846,7 @@ int frcnn_roi_pool_forward_argmax(const float* feat, int B, int Hf, int Wf, int 
     FRCNN_REQUIRE(aligned16(feat) && aligned16(rois) && aligned16(out) && argmax_codes, FRCNN_EINVAL,
                   "roi_pool_forward_argmax: pointers must be 16-byte aligned");
     if (R == 0) return 0;
-    static const bool force_walk = getenv("FRCNN_FWD_WALK") != nullptr;
-    if (roi_pool_stream_supported(C, P, k) && !force_walk)
+    if (roi_pool_stream_supported(C, P, k) && !kForceBinRowWalk)
         return launch_roi_pool_fwd_stream(feat, B, Hf, Wf, C, rois, R, out, argmax_codes, as_stream(stream));
     return launch_codes<0>(feat, B, Hf, Wf, C, rois, R, P, out, argmax_codes, nullptr, nullptr, as_stream(stream));
 }
@@ -855,8 +860,7 @@ int frcnn_roi_pool_backward_argmax(int B, int Hf, int Wf, int C, const float* ro
                   "roi_pool_backward_argmax: pointers must be 16-byte aligned");
     FRCNN_CUDA(cudaMemsetAsync(dfeat, 0, sizeof(float) * (size_t)B * Hf * Wf * C, as_stream(stream)));
     if (R == 0) return 0;
-    static const bool force_walk = getenv("FRCNN_BWD_WALK") != nullptr;  // A/B switch: the older bin-row walk
-    if (roi_pool_stream_supported(C, P, k) && !force_walk)
+    if (roi_pool_stream_supported(C, P, k) && !kForceBinRowWalk)
         return launch_roi_pool_bwd_stream(B, Hf, Wf, C, rois, R, dy, argmax_codes, dfeat, as_stream(stream));
     return launch_codes<1>(nullptr, B, Hf, Wf, C, rois, R, P, nullptr, const_cast<unsigned char*>(argmax_codes), dy, dfeat,
                            as_stream(stream));

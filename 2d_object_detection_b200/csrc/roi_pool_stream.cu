@@ -22,7 +22,6 @@
 // RoIs whose x-samples span more than 51 feature columns do not fit the ring; they take a plain gather path.
 #include <cuda.h>
 #include <cudaTypedefs.h>
-#include <stdlib.h>
 
 #include "roi_axis.cuh"
 
@@ -944,382 +943,6 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads)
 }
 
 
-// ================================================================================================
-// Persistent variant of the forward walk.  The kernel above pays, per RoI, for a prologue every warp waits on and for
-// one exposed L2 -> shared-memory latency before the first row can be interpolated.  Here a CTA (4 warps, 256 channels)
-// stays resident and fetches (RoI, channel chunk) items from a global counter; the tables of item n + 1 are computed by
-// one warp (rotating duty) while all warps work on item n, into a double-buffered "park" guarded by two mbarrier pairs;
-// and every warp's copy pipeline simply runs on into the next item: its ring has four fixed 13-pixel slots, a row of an
-// item occupies m = 1, 2 or 4 consecutive slots (aligned to m), producer and consumer replay the same cursor rule, and a
-// 4-bit busy mask says when a slot group may be staged again -- so the first rows of the next RoI arrive while the last
-// crop rows of the current one are still being emitted.
-// ================================================================================================
-constexpr int kPSlotPix = 13;
-constexpr int kPSlots = 4;
-constexpr int kPSlotBytes = kPSlotPix * kPixBytes;
-
-struct Park {
-    int4 xt[kS];          // {left pixel byte offset in an entry (after the optional zero pixel), 0, x_lerp bits, 0}
-    float ylerp[kS];
-    int rows[2 * kS];
-    int item;             // -1: no more work
-    int n_rows, box, first_px, m, wide, n_before, n_after, b, r, ch0, pix0;  // pix0: pixel index of (row 0, cmin)
-    unsigned prog_lo, prog_hi;
-    int xlo[kS], xhi[kS], xok[kS], ylo[kS], yhi[kS], yok[kS];  // plain sample tables (wide path)
-    float xlerp[kS];
-};
-
-struct PersistShared {
-    Park park[2];
-    unsigned long long tab_full[2], tab_empty[2];
-    unsigned long long full[kWarps][kPSlots];
-};
-
-// Tables of the next item (one warp): fetch its index, then the same column / row analysis as the prologue above.
-__device__ __forceinline__ void persist_make_tables(Park* pk, unsigned* counter, int n_items, int nchunk, int R, int Hf, int Wf,
-                                                 const float4* __restrict__ rois) {
-    const int lane = threadIdx.x & 31;
-    const unsigned all = 0xffffffffu;
-    int item = 0;
-    if (lane == 0) item = (int)atomicAdd(counter, 1u);
-    item = __shfl_sync(all, item, 0);
-    if (item >= n_items) {
-        if (lane == 0) pk->item = -1;
-        return;
-    }
-    const int br = item / nchunk, ch0 = (item - br * nchunk) * kChunk, b = br / R, r = br - b * R;
-    const float4 roi = rois[br];
-    const Sample xs = sample_axis(roi.x, roi.z, Wf, lane);
-    const Sample ys = sample_axis(roi.y, roi.w, Hf, lane);
-    const Span sp = column_span(xs, lane);
-    const int first_px = sp.any_outside ? 1 : 0;
-    int box = 0;
-#pragma unroll
-    for (int i = 0; i < kNumBoxes; ++i) box += (sp.need > box_width(i)) ? 1 : 0;
-    int W = 0;
-#pragma unroll
-    for (int i = 0; i < kNumBoxes; ++i) W = (box == i) ? box_width(i) : W;
-    const int px = W + first_px;
-    const bool wide = box >= kNumBoxes || px > kPSlots * kPSlotPix || sp.need == 0;
-    const int m = px <= kPSlotPix ? 1 : px <= 2 * kPSlotPix ? 2 : 4;
-    if (lane < kS) {
-        const int lerp = xs.ok ? __float_as_int(xs.lerp) : 0;
-        pk->xt[lane] = make_int4(xs.ok ? (xs.lo - sp.cmin + first_px) * kPixBytes : 0, 0, lerp, 0);
-        pk->xlo[lane] = xs.lo; pk->xhi[lane] = xs.hi; pk->xok[lane] = xs.ok; pk->xlerp[lane] = xs.lerp;
-        pk->ylo[lane] = ys.lo; pk->yhi[lane] = ys.hi; pk->yok[lane] = ys.ok; pk->ylerp[lane] = ys.lerp;
-    }
-    const bool v = lane < kS && ys.ok;
-    const int c = ys.lo;
-    const int pv_i = __shfl_up_sync(all, (int)v, 1);
-    const bool pv = pv_i != 0 && lane > 0;
-    const int pc = __shfl_up_sync(all, c, 1);
-    const bool reuse = v && pv && c == pc;
-    const bool shift = v && pv && c == pc + 1;
-    const bool load2 = v && !reuse && !shift;
-    const unsigned lt = (1u << lane) - 1u;
-    const unsigned m1 = __ballot_sync(all, shift || load2), m2 = __ballot_sync(all, load2);
-    const int off = __popc(m1 & lt) + __popc(m2 & lt);
-    const unsigned mv = __ballot_sync(all, v);
-    const int last = Hf - 1;
-    if (load2) {
-        pk->rows[off] = c;
-        pk->rows[off + 1] = min(c + 1, last);
-    } else if (shift) {
-        pk->rows[off] = min(c + 1, last);
-    }
-    const int bitpos = off + (load2 ? 2 : shift ? 1 : 0) + __popc(mv & lt);
-    const unsigned prog_lo = __reduce_or_sync(all, (v && bitpos < 32) ? (1u << bitpos) : 0u);
-    const unsigned prog_hi = __reduce_or_sync(all, (v && bitpos >= 32) ? (1u << (bitpos - 32)) : 0u);
-    const int n_before = __popc(__ballot_sync(all, lane < kS && !v && !(mv & lt)));
-    if (lane == 0) {
-        pk->item = item;
-        pk->n_rows = wide ? 0 : __popc(m1) + __popc(m2);
-        pk->box = box;
-        pk->first_px = first_px;
-        pk->m = m;
-        pk->wide = wide ? 1 : 0;
-        pk->n_before = n_before;
-        pk->n_after = kS - n_before - __popc(mv);
-        pk->b = b;
-        pk->r = r;
-        pk->ch0 = ch0;
-        pk->pix0 = b * Hf * Wf + sp.cmin;
-        pk->prog_lo = prog_lo;
-        pk->prog_hi = prog_hi;
-    }
-    __syncwarp();
-}
-
-// Per-warp pipeline state.  Everything here is warp-uniform and is kept provably so (values read from shared memory pass
-// through __reduce_or_sync), so that ptxas holds it in uniform registers instead of the 128 vector registers.
-struct PWalk {
-    unsigned ring;        // shared address of this warp's ring
-    unsigned full0;       // shared address of this warp's full[0]
-    // producer side (the walk position that is staged next)
-    int pn, p_k, p_n, p_m, p_active, pc;
-    // consumer side
-    int cn, cc;
-    unsigned busy, cphase;
-};
-
-// Stage as many further rows as the ring takes, running on into the next item when its tables are there.
-__device__ __forceinline__ void persist_stage(PWalk& w, PersistShared& sh, const TensorMaps& maps, int Wf) {
-    const int lane = threadIdx.x & 31;
-    const unsigned all = 0xffffffffu;
-#pragma unroll 1
-    for (int guard = 0; guard < 2 * kPSlots; ++guard) {
-        if (!w.p_active) {
-            if (w.pn > w.cn + 1) return;  // that park still belongs to the item before the consumer's
-            const unsigned bar = smem_u32(&sh.tab_full[w.pn & 1]);
-            if (!mbar_test(bar, (unsigned)(w.pn >> 1) & 1u)) return;
-            const Park& pk = sh.park[w.pn & 1];
-            const int item = __reduce_or_sync(all, pk.item);
-            if (item < 0) return;
-            w.p_n = __reduce_or_sync(all, pk.n_rows);
-            w.p_m = __reduce_or_sync(all, pk.m);
-            w.p_k = 0;
-            if (w.p_n == 0) {  // nothing to stage (wide path or no row inside the map)
-                ++w.pn;
-                continue;
-            }
-            w.p_active = 1;
-        }
-        int c = (w.pc + w.p_m - 1) & ~(w.p_m - 1);
-        if (c >= kPSlots) c = 0;
-        const unsigned mask = ((1u << w.p_m) - 1u) << c;
-        if (w.busy & mask) return;
-        if (lane == 0) {  // the TMA parameters come straight from the park
-            const Park& pk = sh.park[w.pn & 1];
-            const unsigned bar = w.full0 + c * 8;
-            const int box = pk.box;
-            mbar_expect_tx(bar, (unsigned)(box_width(box) * kPixBytes));
-            tma_box_g2s(w.ring + c * kPSlotBytes + pk.first_px * kPixBytes, &maps.box[box], pk.ch0 + (int)(threadIdx.x >> 5) * kWarpCh,
-                        pk.pix0 + pk.rows[w.p_k] * Wf, bar);
-        }
-        w.busy |= mask;
-        w.pc = c + w.p_m;
-        if (++w.p_k == w.p_n) {
-            w.p_active = 0;
-            ++w.pn;
-        }
-    }
-}
-
-// x-interpolate the next staged row of the consumer's item (m slots per row, zero pixel in front if `first`).
-__device__ __forceinline__ void persist_load_row(PWalk& w, PersistShared& sh, const TensorMaps& maps, int Wf, u64 (&X)[kS],
-                                                 const int (&aoff)[kS], const Park& pk, int m, int first, u64 one) {
-    int c = (w.cc + m - 1) & ~(m - 1);
-    if (c >= kPSlots) c = 0;
-#ifdef FRCNN_DEBUG_SPIN
-    {
-        unsigned long long t0, t1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        while (!mbar_test(w.full0 + c * 8, (w.cphase >> c) & 1u)) {
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 20000000ull) {
-                if ((threadIdx.x & 31) == 0)
-                    printf("row wait stuck: block %d warp %d c %d m %d cn %d pn %d p_k %d p_n %d p_m %d p_active %d pc %d cc %d busy %x cphase %x item %d/%d nrows %d/%d\n",
-                           blockIdx.x, threadIdx.x >> 5, c, m, w.cn, w.pn, w.p_k, w.p_n, w.p_m, w.p_active, w.pc, w.cc, w.busy, w.cphase,
-                           sh.park[0].item, sh.park[1].item, sh.park[0].n_rows, sh.park[1].n_rows);
-                __trap();
-            }
-        }
-    }
-#else
-    mbar_wait(w.full0 + c * 8, (w.cphase >> c) & 1u);
-#endif
-    w.cphase ^= 1u << c;
-    const unsigned slot_off = __reduce_or_sync(0xffffffffu, (unsigned)(c * kPSlotBytes));
-    if (first) sts64(w.ring + slot_off + (threadIdx.x & 31) * 8, 0ull);  // the zero pixel in front of this entry
-#pragma unroll
-    for (int i = 0; i < kS; ++i) {
-        u64 l, r;
-        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(l) : "r"(aoff[i] + slot_off));
-        asm volatile("ld.shared.b64 %0, [%1+256];" : "=l"(r) : "r"(aoff[i] + slot_off));
-        const float xl = __int_as_float(pk.xt[i].z);  // (weights stay in shared memory: the register file is full)
-        X[i] = lerp2(l, r, pack2(xl, xl), one);
-    }
-    __syncwarp();  // every lane has consumed its operands: the slots may be overwritten
-    w.busy &= ~(((1u << m) - 1u) << c);
-    w.cc = c + m;
-    persist_stage(w, sh, maps, Wf);
-}
-
-template <int kC, bool kCodes>
-__global__ void __launch_bounds__(kThreads, 512 / kThreads)
-    roi_pool_fwd_persist_kernel(const __grid_constant__ TensorMaps maps, const float* __restrict__ feat, int Hf, int Wf, int C_,
-                                const float4* __restrict__ rois, int R, int nchunk, int n_items, float* __restrict__ out,
-                                unsigned char* __restrict__ codes, unsigned* __restrict__ counters) {
-    const int C = kC ? kC : C_;
-    extern __shared__ __align__(128) unsigned char smem[];
-    PersistShared& sh = *reinterpret_cast<PersistShared*>(smem);
-    unsigned char* ring = smem + (sizeof(PersistShared) + 127) / 128 * 128;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned all = 0xffffffffu;
-    if (tid < kWarps * kPSlots) mbar_init(smem_u32(&sh.full[0][0]) + tid * 8, 1);
-    else if (tid < kWarps * kPSlots + 2) mbar_init(smem_u32(&sh.tab_full[tid - kWarps * kPSlots]), 1);
-    else if (tid < kWarps * kPSlots + 4) mbar_init(smem_u32(&sh.tab_empty[tid - kWarps * kPSlots - 2]), kWarps);
-    if (tid < kWarps * kPSlots + 4) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncthreads();
-    if (warp == 0) {  // the first item of this CTA
-        persist_make_tables(&sh.park[0], counters, n_items, nchunk, R, Hf, Wf, rois);
-        if (lane == 0) mbar_arrive(smem_u32(&sh.tab_full[0]));
-    }
-
-    PWalk w;
-    w.ring = smem_u32(ring) + warp * (kPSlots * kPSlotBytes);
-    w.full0 = smem_u32(&sh.full[warp][0]);
-    w.pn = 0; w.p_k = 0; w.p_n = 0; w.p_m = 1; w.p_active = 0; w.pc = 0;
-    w.cn = 0; w.cc = 0;
-    w.busy = 0u; w.cphase = 0u;
-    u64 one;
-    {
-        const float onef = kOne;
-        one = pack2(onef, onef);
-    }
-#pragma unroll 1
-    for (;;) {
-        const int p = w.cn & 1;
-        mbar_wait(smem_u32(&sh.tab_full[p]), (unsigned)(w.cn >> 1) & 1u);
-        const Park& pk = sh.park[p];
-        if ((int)__reduce_or_sync(all, pk.item) < 0) break;  // (reduce_or returns unsigned)
-        // rotating duty: the tables of the item after this one
-        if (((w.cn + 1) & (kWarps - 1)) == warp) {
-            if (w.cn >= 1) mbar_wait(smem_u32(&sh.tab_empty[p ^ 1]), (unsigned)((w.cn - 1) >> 1) & 1u);
-            persist_make_tables(&sh.park[p ^ 1], counters, n_items, nchunk, R, Hf, Wf, rois);
-            if (lane == 0) mbar_arrive(smem_u32(&sh.tab_full[p ^ 1]));
-        }
-        const int b = pk.b, r = pk.r, ch = pk.ch0 + warp * kWarpCh + lane * 2;
-        float2* optr = reinterpret_cast<float2*>(out + ((size_t)b * R + r) * (kP * kP) * C + ch);
-        unsigned char* cptr = kCodes ? codes + ((size_t)b * R + r) * (kP * kP) * (C / 4) + ch / 4 : nullptr;
-        const int bin_stride = C / 2;
-        if (__reduce_or_sync(all, pk.wide)) {  // rare: one bilinear gather per sample, same arithmetic
-            const float* fb = feat + (size_t)b * Hf * Wf * C + ch;
-#pragma unroll 1
-            for (int bin = 0; bin < kP * kP; ++bin) {
-                const int py = bin / kP, px = bin - py * kP;
-                float2 best = make_float2(0.0f, 0.0f);
-                unsigned cw = 0u;
-#pragma unroll 1
-                for (int s4 = 0; s4 < 4; ++s4) {
-                    const int sy = 2 * py + (s4 >> 1), sx = 2 * px + (s4 & 1);
-                    float2 val = make_float2(0.0f, 0.0f);
-                    if (pk.yok[sy] && pk.xok[sx]) {
-                        const float* top = fb + (size_t)pk.ylo[sy] * Wf * C;
-                        const float* bot = fb + (size_t)pk.yhi[sy] * Wf * C;
-                        const size_t xl = (size_t)pk.xlo[sx] * C, xh = (size_t)pk.xhi[sx] * C;
-                        const u64 tl = *reinterpret_cast<const u64*>(top + xl), tr = *reinterpret_cast<const u64*>(top + xh);
-                        const u64 bl = *reinterpret_cast<const u64*>(bot + xl), br = *reinterpret_cast<const u64*>(bot + xh);
-                        const u64 wxx = pack2(pk.xlerp[sx], pk.xlerp[sx]), wy = pack2(pk.ylerp[sy], pk.ylerp[sy]);
-                        val = unpack2(lerp2(lerp2(tl, tr, wxx, one), lerp2(bl, br, wxx, one), wy, one));
-                    }
-                    if (s4 == 0) {
-                        best = val;
-                    } else {
-                        take_if_greater(best.x, cw, val.x, (unsigned)s4, 0);
-                        take_if_greater(best.y, cw, val.y, (unsigned)s4, 2);
-                    }
-                }
-                __stcs(optr + (size_t)bin * bin_stride, best);
-                if (kCodes) {
-                    const unsigned pw = __shfl_xor_sync(all, cw, 1);
-                    if (!(lane & 1)) cptr[(size_t)bin * (C / 4)] = (unsigned char)((cw & 15u) | ((pw & 15u) << 4));
-                }
-            }
-        } else {
-            u64 X0[kS], X1[kS];  // (declared per item: nothing vector-sized is live across the table-making call)
-#pragma unroll
-            for (int i = 0; i < kS; ++i) X0[i] = X1[i] = 0ull;
-            float2 M[kP];
-#pragma unroll
-            for (int j = 0; j < kP; ++j) M[j] = make_float2(0.0f, 0.0f);
-            int aoff[kS];
-#pragma unroll
-            for (int i = 0; i < kS; ++i) aoff[i] = pk.xt[i].x + (int)w.ring + lane * 8;
-            const int n_rows = __reduce_or_sync(all, pk.n_rows);
-            const int m = __reduce_or_sync(all, pk.m), first = __reduce_or_sync(all, pk.first_px);
-            u64 prog = ((u64)__reduce_or_sync(all, pk.prog_hi) << 32) | __reduce_or_sync(all, pk.prog_lo);
-            const int n_before = pk.n_before, n_after = pk.n_after;
-            int sy = 0;
-            unsigned ca = 0u, cb = 0u;
-            auto emit = [&](const u64 (&T)[kS], const u64 (&Bm)[kS], bool outside) {
-                if (!(sy & 1)) {
-                    ca = cb = 0u;
-                    if (outside) {
-#pragma unroll
-                        for (int j = 0; j < kP; ++j) M[j] = make_float2(0.0f, 0.0f);
-                    } else {
-                        crop_row<true, kCodes>(T, Bm, pk.ylerp[sy], one, M, ca, cb);
-                    }
-                } else {
-                    if (outside) {
-#pragma unroll
-                        for (int j = 0; j < kP; ++j) {
-                            if (kCodes) {
-                                flag_if_greater(M[j].x, ca, 0.0f, 2u << (4 * j));
-                                flag_if_greater(M[j].y, ca, 0.0f, 8u << (4 * j));
-                            } else {
-                                M[j] = make_float2(fmaxf(M[j].x, 0.0f), fmaxf(M[j].y, 0.0f));
-                            }
-                        }
-                    } else {
-                        crop_row<false, kCodes>(T, Bm, pk.ylerp[sy], one, M, ca, cb);
-                    }
-#pragma unroll
-                    for (int j = 0; j < kP; ++j) __stcs(optr + j * bin_stride, M[j]);
-                    optr += kP * bin_stride;
-                    if (kCodes) {
-                        const unsigned cw = codes_from_flags(ca, cb);
-                        const unsigned pw = __shfl_xor_sync(all, cw, 1);
-                        if (!(lane & 1)) {
-#pragma unroll
-                            for (int j = 0; j < kP; ++j)
-                                cptr[j * (C / 4)] = (unsigned char)(((cw >> (4 * j)) & 15u) | (((pw >> (4 * j)) & 15u) << 4));
-                        }
-                        cptr += kP * (C / 4);
-                    }
-                }
-                ++sy;
-            };
-            persist_stage(w, sh, maps, Wf);
-            for (int i = 0; i < n_before; ++i) emit(X0, X1, true);
-#pragma unroll 1
-            for (int k = 0; k < n_rows; k += 2) {
-                persist_load_row(w, sh, maps, Wf, X0, aoff, pk, m, first, one);
-                prog >>= 1;
-                while (prog & 1ull) {
-                    emit(X1, X0, false);
-                    prog >>= 1;
-                }
-                if (k + 1 < n_rows) {
-                    persist_load_row(w, sh, maps, Wf, X1, aoff, pk, m, first, one);
-                    prog >>= 1;
-                    while (prog & 1ull) {
-                        emit(X0, X1, false);
-                        prog >>= 1;
-                    }
-                }
-            }
-            for (int i = 0; i < n_after; ++i) emit(X0, X1, true);
-        }
-        // done with this item's tables
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&sh.tab_empty[p]));
-        ++w.cn;
-        if (w.pn < w.cn) w.pn = w.cn;  // (an item without rows was skipped by the consumer before the producer looked at it)
-    }
-    // the last CTA to leave resets the work counter for the next launch
-    __syncthreads();
-    if (tid == 0) {
-        const unsigned done = atomicAdd(counters + 1, 1u);
-        if (done == gridDim.x - 1) {
-            counters[0] = 0u;
-            counters[1] = 0u;
-            __threadfence();
-        }
-    }
-}
-
 // Host side: the eight tensor maps of a feature tensor, cached by (pointer, shape).
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1448,48 +1071,6 @@ int launch_roi_pool_fwd_stream(const float* feat, int B, int Hf, int Wf, int C, 
     const int rc = get_tensor_maps(feat, (long long)B * Hf * Wf, C, dev, &maps);
     if (rc) return rc;
     const float4* r4 = (const float4*)rois;
-    static const bool persist = getenv("FRCNN_FWD_PERSIST") != nullptr;
-    if (persist) {
-        const size_t psmem = (sizeof(PersistShared) + 127) / 128 * 128 + (size_t)kWarps * kPSlots * kPSlotBytes;
-        static bool pconf[64] = {};
-        static unsigned* counters[64] = {};
-        FRCNN_REQUIRE(dev >= 0 && dev < 64, FRCNN_ELIMIT, "roi_pool_forward: device index beyond 63");
-        if (!pconf[dev]) {
-            FRCNN_CUDA(cudaFuncSetAttribute(roi_pool_fwd_persist_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-            FRCNN_CUDA(cudaFuncSetAttribute(roi_pool_fwd_persist_kernel<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-            FRCNN_CUDA(cudaFuncSetAttribute(roi_pool_fwd_persist_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-            FRCNN_CUDA(cudaFuncSetAttribute(roi_pool_fwd_persist_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-            // one work counter pair per stream slot (launches on different streams may overlap); reset by the kernel itself
-            FRCNN_CUDA(cudaMalloc(&counters[dev], 64 * 2 * sizeof(unsigned)));
-            FRCNN_CUDA(cudaMemset(counters[dev], 0, 64 * 2 * sizeof(unsigned)));
-            pconf[dev] = true;
-        }
-        static cudaStream_t slot_stream[64][64] = {};
-        static int slots_used[64] = {};
-        int slot = -1;
-        for (int i = 0; i < slots_used[dev]; ++i)
-            if (slot_stream[dev][i] == st) slot = i;
-        if (slot < 0) {
-            FRCNN_REQUIRE(slots_used[dev] < 64, FRCNN_ELIMIT, "roi_pool_forward: more than 64 streams per device");
-            slot = slots_used[dev]++;
-            slot_stream[dev][slot] = st;
-        }
-        int sms = 0;
-        FRCNN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        const int n_items = B * R * nchunk;
-        const int per_sm = 512 / kThreads;
-        const int ctas = n_items < per_sm * sms ? n_items : per_sm * sms;
-        unsigned* ctr = counters[dev] + 2 * slot;
-        if (codes) {
-            if (C == 1024) roi_pool_fwd_persist_kernel<1024, true><<<ctas, kThreads, psmem, st>>>(*maps, feat, Hf, Wf, C, r4, R, nchunk, n_items, out, codes, ctr);
-            else roi_pool_fwd_persist_kernel<0, true><<<ctas, kThreads, psmem, st>>>(*maps, feat, Hf, Wf, C, r4, R, nchunk, n_items, out, codes, ctr);
-        } else {
-            if (C == 1024) roi_pool_fwd_persist_kernel<1024, false><<<ctas, kThreads, psmem, st>>>(*maps, feat, Hf, Wf, C, r4, R, nchunk, n_items, out, nullptr, ctr);
-            else roi_pool_fwd_persist_kernel<0, false><<<ctas, kThreads, psmem, st>>>(*maps, feat, Hf, Wf, C, r4, R, nchunk, n_items, out, nullptr, ctr);
-        }
-        FRCNN_LAUNCH_CHECK("roi_pool_fwd_persist_kernel");
-        return 0;
-    }
     const dim3 grid(R * nchunk, B);
     if (codes) {
         if (C == 1024) roi_pool_fwd_stream_kernel<1024, true><<<grid, kThreads, smem, st>>>(*maps, feat, Hf, Wf, C, r4, R, nchunk, out, codes);

@@ -187,7 +187,7 @@ extern "C" {
 size_t frcnn_sample_indices_workspace_bytes(int B, int N) { return sizeof(int) * 2 * (size_t)(B > 0 ? B : 0) * (size_t)(N > 0 ? N : 0) + 16; }
 
 int frcnn_sample_and_gather(const float* target_labels, int B, int N, int num_classes_plus_1, int num_samples,
-                            float foreground_proportion, uint64_t seed, int64_t* indices, int32_t* counts,
+                            double foreground_proportion, uint64_t seed, int64_t* indices, int32_t* counts,
                             const float* pred_scores, const float* target_boxes, const float* pred_boxes, float* out_labels,
                             float* out_scores, float* out_target_boxes, float* out_pred_boxes, void* workspace,
                             size_t workspace_bytes, frcnn_stream_t stream) {
@@ -198,10 +198,16 @@ int frcnn_sample_and_gather(const float* target_labels, int B, int N, int num_cl
                   FRCNN_EINVAL, "sample_and_gather: an output was requested without its source tensor");
     FRCNN_REQUIRE(workspace && workspace_bytes >= frcnn_sample_indices_workspace_bytes(B, N), FRCNN_EWORKSPACE,
                   "sample_and_gather: workspace too small");
+    FRCNN_REQUIRE(foreground_proportion >= 0.0 && foreground_proportion <= 1.0, FRCNN_EINVAL,
+                  "sample_and_gather: foreground_proportion %g outside [0, 1]", foreground_proportion);
     // tf.math.round(num_samples * foreground_proportion): the product is a Python float (double), then round-half-even
-    const int quota = (int)nearbyint((double)num_samples * (double)foreground_proportion);
+    int quota = (int)nearbyint((double)num_samples * foreground_proportion);
+    quota = quota < 0 ? 0 : quota > num_samples ? num_samples : quota;
+    // the chunked selection keeps the best `quota` keys at the front of a kSortCap-entry buffer and needs room for new ones
+    FRCNN_REQUIRE(quota < kSortCap, FRCNN_ELIMIT, "sample_and_gather: foreground quota %d >= %d (num_samples * foreground_proportion too large)",
+                  quota, kSortCap);
     sample_gather_kernel<<<B, kSampThreads, 0, as_stream(stream)>>>(
-        target_labels, N, num_classes_plus_1, num_samples, quota < 0 ? 0 : quota, (uint32_t)seed, (uint32_t)(seed >> 32),
+        target_labels, N, num_classes_plus_1, num_samples, quota, (uint32_t)seed, (uint32_t)(seed >> 32),
         (int*)workspace, (long long*)indices, counts, pred_scores, target_boxes, pred_boxes, out_labels, out_scores,
         out_target_boxes, out_pred_boxes);
     FRCNN_LAUNCH_CHECK("sample_gather_kernel");

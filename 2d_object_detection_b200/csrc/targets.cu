@@ -12,8 +12,39 @@ namespace frcnn {
 constexpr int kMaxGt = 1024;
 constexpr int kTgtThreads = 256;
 
+// Label row `g` of an image as generate_targets sees it.  kObj = false: the row itself (L = nc + 1 columns).
+// kObj = true: the RPN's objectness labels, rpn_detector.py:141 folded in --
+//   one_hot(cast(reduce_sum(gt_labels, -1), int32), depth=2): a padding row (sum 0) becomes [1, 0] and is therefore NOT
+//   removed by training.py:43-45 (trap T11); a one-hot row (sum 1) becomes [0, 1]; any other integer gives [0, 0].
+struct LabelRow {
+    const float* row;  // the input row, Lin columns
+    int Lin;
+    int obj_idx;       // kObj: the one_hot index
+    template <bool kObj>
+    __device__ __forceinline__ static LabelRow load(const float* gt_labels, size_t row_index, int Lin) {
+        LabelRow r{gt_labels + row_index * Lin, Lin, 0};
+        if (kObj) {
+            float s = 0.0f;
+            for (int c = 0; c < Lin; ++c) s = fadd(s, r.row[c]);  // tf.reduce_sum, left to right
+            r.obj_idx = (int)s;                                    // tf.cast float -> int32 truncates
+        }
+        return r;
+    }
+    template <bool kObj>
+    __device__ __forceinline__ float at(int c) const {
+        return kObj ? ((c == obj_idx) ? 1.0f : 0.0f) : row[c];
+    }
+    template <bool kObj>
+    __device__ __forceinline__ float sum(int L) const {  // L = columns generate_targets sees (2 for objectness)
+        float s = 0.0f;
+        for (int c = 0; c < L; ++c) s = fadd(s, at<kObj>(c));
+        return s;
+    }
+};
+
+template <bool kObj>
 __global__ void __launch_bounds__(kTgtThreads)
-    match_kernel(const float* __restrict__ gt_labels, const float4* __restrict__ gt_boxes, int G, int L,
+    match_kernel(const float* __restrict__ gt_labels, int Lin, const float4* __restrict__ gt_boxes, int G, int L,
                  const float4* __restrict__ regions, int regions_batched, int N, float img_h, float img_w,
                  float* __restrict__ max_iou, int32_t* __restrict__ argmax, unsigned long long* __restrict__ gmax,
                  int32_t* __restrict__ gt_src) {
@@ -25,8 +56,7 @@ __global__ void __launch_bounds__(kTgtThreads)
     const int b = blockIdx.y;
     // training.py:43-45: drop rows whose label sum is 0, order preserved (ssrc doubles as the flag array first)
     for (int g = threadIdx.x; g < G; g += blockDim.x) {
-        float s = 0.0f;
-        for (int c = 0; c < L; ++c) s = fadd(s, gt_labels[((size_t)b * G + g) * L + c]);
+        const float s = LabelRow::load<kObj>(gt_labels, (size_t)b * G + g, Lin).template sum<kObj>(L);
         sflag[g] = (s != 0.0f) ? 1 : 0;
     }
     __syncthreads();
@@ -74,8 +104,9 @@ __global__ void __launch_bounds__(kTgtThreads)
     if (threadIdx.x == 0 && blockIdx.x == 0) gt_src[(size_t)b * (G + 1) + G] = gp;  // count in the extra slot
 }
 
+template <bool kObj>
 __global__ void __launch_bounds__(kTgtThreads)
-    labels_kernel(const float* __restrict__ gt_labels, const float4* __restrict__ gt_boxes, int G, int nc,
+    labels_kernel(const float* __restrict__ gt_labels, int Lin, const float4* __restrict__ gt_boxes, int G, int nc,
                   const float4* __restrict__ regions, int regions_batched, int N, float img_h, float img_w, float fg_lo,
                   float fg_hi, float bg_lo, float bg_hi, const float* __restrict__ max_iou,
                   const int32_t* __restrict__ argmax, const unsigned long long* __restrict__ gmax,
@@ -95,14 +126,14 @@ __global__ void __launch_bounds__(kTgtThreads)
     float4* tb = target_boxes + ((size_t)b * N + n) * nc;
     if (fg) {
         const int g = gt_src[(size_t)b * (G + 1) + argmax[(size_t)b * N + n]];
-        const float* gl = gt_labels + ((size_t)b * G + g) * L;
+        const LabelRow gl = LabelRow::load<kObj>(gt_labels, (size_t)b * G + g, Lin);
         const float4 r = gt_boxes[(size_t)b * G + g];
         const float4 gabs = make_float4(fmul(r.x, img_w), fmul(r.y, img_h), fmul(r.z, img_w), fmul(r.w, img_h));
         const float4 reg = regions[regions_batched ? (size_t)b * N + n : (size_t)n];
         const float4 enc = encode_box(gabs, reg);  // :68-69
-        tl[0] = gl[0];
+        tl[0] = gl.at<kObj>(0);
         for (int c = 0; c < nc; ++c) {
-            const float l = gl[1 + c];
+            const float l = gl.at<kObj>(1 + c);
             tl[1 + c] = l;  // :61,65 foreground overrides background
             tb[c] = (l != 0.0f) ? enc : make_float4(0.f, 0.f, 0.f, 0.f);  // :70-75 masked by labels[:,1:]
         }
@@ -113,6 +144,15 @@ __global__ void __launch_bounds__(kTgtThreads)
             tb[c] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
+}
+
+// rpn_detector.py:141 on its own (the Python helper rpn_objectness_labels): [rows, Lin] -> [rows, 2]
+__global__ void objectness_kernel(const float* __restrict__ gt_labels, long long rows, int Lin, float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const LabelRow r = LabelRow::load<true>(gt_labels, (size_t)i, Lin);
+    out[2 * i] = r.at<true>(0);
+    out[2 * i + 1] = r.at<true>(1);
 }
 
 struct TgtWs {
@@ -149,11 +189,12 @@ size_t frcnn_generate_targets_workspace_bytes(int B, int N) {
     return carve_tgt_ws(nullptr, B, N, kMaxGt).bytes;
 }
 
-int frcnn_generate_targets(const float* gt_labels, const float* gt_boxes, int B, int G, int nc, const float* regions,
-                           int regions_batched, int N, float img_h, float img_w, float fg_lo, float fg_hi, float bg_lo,
-                           float bg_hi, float* target_labels, float* target_boxes, float* max_iou, int32_t* argmax,
-                           void* workspace, size_t workspace_bytes, frcnn_stream_t stream) {
-    FRCNN_REQUIRE(B > 0 && G >= 0 && nc > 0 && N >= 0, FRCNN_EINVAL, "generate_targets: bad shape");
+static int generate_targets_impl(bool objectness, const float* gt_labels, int Lin, const float* gt_boxes, int B, int G, int nc,
+                                 const float* regions, int regions_batched, int N, float img_h, float img_w, float fg_lo,
+                                 float fg_hi, float bg_lo, float bg_hi, float* target_labels, float* target_boxes,
+                                 float* max_iou, int32_t* argmax, void* workspace, size_t workspace_bytes,
+                                 frcnn_stream_t stream) {
+    FRCNN_REQUIRE(B > 0 && G >= 0 && nc > 0 && N >= 0 && Lin >= 1, FRCNN_EINVAL, "generate_targets: bad shape");
     FRCNN_REQUIRE(G <= kMaxGt, FRCNN_ELIMIT, "generate_targets: G = %d exceeds the %d limit", G, kMaxGt);
     FRCNN_REQUIRE(B <= 65535, FRCNN_ELIMIT, "generate_targets: B > 65535");
     FRCNN_REQUIRE(aligned16(gt_boxes) && aligned16(regions) && aligned16(target_boxes) && target_labels, FRCNN_EINVAL,
@@ -167,13 +208,51 @@ int frcnn_generate_targets(const float* gt_labels, const float* gt_boxes, int B,
     int32_t* am = argmax ? argmax : w.argmax;
     FRCNN_CUDA(cudaMemsetAsync(w.gmax, 0, sizeof(unsigned long long) * (size_t)B, st));
     const dim3 grid((N + kTgtThreads - 1) / kTgtThreads, B);
-    match_kernel<<<grid, kTgtThreads, 0, st>>>(gt_labels, (const float4*)gt_boxes, G, nc + 1, (const float4*)regions,
-                                               regions_batched, N, img_h, img_w, mi, am, w.gmax, w.gt_src);
+    if (objectness) {
+        match_kernel<true><<<grid, kTgtThreads, 0, st>>>(gt_labels, Lin, (const float4*)gt_boxes, G, nc + 1, (const float4*)regions,
+                                                         regions_batched, N, img_h, img_w, mi, am, w.gmax, w.gt_src);
+        FRCNN_LAUNCH_CHECK("match_kernel<objectness>");
+        labels_kernel<true><<<grid, kTgtThreads, 0, st>>>(gt_labels, Lin, (const float4*)gt_boxes, G, nc, (const float4*)regions,
+                                                          regions_batched, N, img_h, img_w, fg_lo, fg_hi, bg_lo, bg_hi, mi, am,
+                                                          w.gmax, w.gt_src, target_labels, (float4*)target_boxes);
+        FRCNN_LAUNCH_CHECK("labels_kernel<objectness>");
+        return 0;
+    }
+    match_kernel<false><<<grid, kTgtThreads, 0, st>>>(gt_labels, Lin, (const float4*)gt_boxes, G, nc + 1, (const float4*)regions,
+                                                      regions_batched, N, img_h, img_w, mi, am, w.gmax, w.gt_src);
     FRCNN_LAUNCH_CHECK("match_kernel");
-    labels_kernel<<<grid, kTgtThreads, 0, st>>>(gt_labels, (const float4*)gt_boxes, G, nc, (const float4*)regions,
-                                                regions_batched, N, img_h, img_w, fg_lo, fg_hi, bg_lo, bg_hi, mi, am,
-                                                w.gmax, w.gt_src, target_labels, (float4*)target_boxes);
+    labels_kernel<false><<<grid, kTgtThreads, 0, st>>>(gt_labels, Lin, (const float4*)gt_boxes, G, nc, (const float4*)regions,
+                                                       regions_batched, N, img_h, img_w, fg_lo, fg_hi, bg_lo, bg_hi, mi, am,
+                                                       w.gmax, w.gt_src, target_labels, (float4*)target_boxes);
     FRCNN_LAUNCH_CHECK("labels_kernel");
+    return 0;
+}
+
+int frcnn_generate_targets(const float* gt_labels, const float* gt_boxes, int B, int G, int nc, const float* regions,
+                           int regions_batched, int N, float img_h, float img_w, float fg_lo, float fg_hi, float bg_lo,
+                           float bg_hi, float* target_labels, float* target_boxes, float* max_iou, int32_t* argmax,
+                           void* workspace, size_t workspace_bytes, frcnn_stream_t stream) {
+    return generate_targets_impl(false, gt_labels, nc + 1, gt_boxes, B, G, nc, regions, regions_batched, N, img_h, img_w,
+                                 fg_lo, fg_hi, bg_lo, bg_hi, target_labels, target_boxes, max_iou, argmax, workspace,
+                                 workspace_bytes, stream);
+}
+
+int frcnn_generate_targets_objectness(const float* gt_labels, const float* gt_boxes, int B, int G, int num_classes_plus_1,
+                                      const float* regions, int regions_batched, int N, float img_h, float img_w,
+                                      float fg_lo, float fg_hi, float bg_lo, float bg_hi, float* target_labels,
+                                      float* target_boxes, float* max_iou, int32_t* argmax, void* workspace,
+                                      size_t workspace_bytes, frcnn_stream_t stream) {
+    return generate_targets_impl(true, gt_labels, num_classes_plus_1, gt_boxes, B, G, 1, regions, regions_batched, N, img_h,
+                                 img_w, fg_lo, fg_hi, bg_lo, bg_hi, target_labels, target_boxes, max_iou, argmax, workspace,
+                                 workspace_bytes, stream);
+}
+
+int frcnn_objectness_labels(const float* gt_labels, int64_t rows, int num_classes_plus_1, float* out, frcnn_stream_t stream) {
+    FRCNN_REQUIRE(rows >= 0 && num_classes_plus_1 >= 1 && (rows == 0 || (gt_labels && out)), FRCNN_EINVAL,
+                  "objectness_labels: bad arguments");
+    if (rows == 0) return 0;
+    objectness_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, as_stream(stream)>>>(gt_labels, rows, num_classes_plus_1, out);
+    FRCNN_LAUNCH_CHECK("objectness_kernel");
     return 0;
 }
 

@@ -120,3 +120,139 @@ class ProposalRoIEngine:
             self._ev_pool[j].record(self.s_pool)
         self._pool_recorded[j] = True
         return self._rois[j], self._roi_scores[j], self._num_valid[j], self.pooled
+
+
+class TrainStepEngine:
+    """Pre-allocated training-path step (BASELINE configs[4]; models/faster_rcnn.py:59-117 minus the conv / Dense layers):
+
+        RPN training filter (rpn_detector.py:201-230)      frcnn_gather_rows x 2
+        proposals (post_processing.py:6-63)                 frcnn_postprocess               (3 kernels)
+        RPN samples (rpn_detector.py:98-160)                frcnn_generate_targets_objectness + frcnn_sample_and_gather
+        RPN losses (faster_rcnn.py:87-93)                   frcnn_sampled_losses
+        ROIPooling forward, arg-max codes saved (:56)       frcnn_roi_pool_forward_argmax
+        regions = to_absolute(rois) (fast_rcnn_detector.py:66)   frcnn_scale_boxes
+        RCNN samples (fast_rcnn_detector.py:71-130)         frcnn_generate_targets + frcnn_sample_and_gather
+        RCNN losses (faster_rcnn.py:94-100)                 frcnn_sampled_losses
+        ROIPooling backward (:103 through :56)              frcnn_roi_pool_backward_argmax
+
+    Every output and workspace is allocated once here; ``step`` only enqueues C-ABI calls on the current stream (no torch
+    op, no allocation, no synchronisation), so it can be captured in a CUDA graph.  The Dense heads between the pooled
+    features and the RCNN predictions are the caller's: ``rcnn_scores`` / ``rcnn_boxes`` / ``d_pooled`` are its tensors
+    (bench.py passes synthetic ones)."""
+
+    KERNELS_PER_STEP = 17  # 2 gathers, 3 postprocess, 2+1 RPN targets/samples, 1 loss, 1 pool fwd, 1 scale, 2+1 RCNN, 1 loss, 1 pool bwd (+ 3 memsets)
+
+    def __init__(self, image_shape, batch, grid_shape, channels, anchors, num_classes, rpn_config, rcnn_config,
+                 max_num_objects=100, pre_nms_top_n=None):
+        from .models.detectors.rpn_detector import _gather_rows, valid_anchor_indices
+        dev = require_cuda()
+        self._lib = lib()
+        self.image_shape = tuple(image_shape)
+        self.B, (self.Hf, self.Wf), self.C = int(batch), grid_shape, int(channels)
+        self.nc = int(num_classes)
+        self.G = int(max_num_objects)
+        self.rpn, self.rcnn = rpn_config, rcnn_config
+        nms = rpn_config["nms"]
+        self.R = int(nms["max_total_size"])
+        self.per_class = int(nms["max_output_size_per_class"])
+        self.P, self.k = int(rcnn_config["roi_pooling"]["pooled_size"]), int(rcnn_config["roi_pooling"]["kernel_size"])
+        self.pre_nms_top_n = int(pre_nms_top_n or 0)
+        a = as_device(anchors)
+        self.N = a.shape[0]
+        self.valid_idx = valid_anchor_indices(a, image_shape)      # static per configuration (one-off synchronisation)
+        self.valid_anchors = _gather_rows(a[None], self.valid_idx)[0]
+        self.Nv = int(self.valid_idx.numel())
+        B, Nv, R, nc, C = self.B, self.Nv, self.R, self.nc, self.C
+        f32 = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)  # noqa: E731
+        i32 = lambda *s: torch.empty(s, dtype=torch.int32, device=dev)    # noqa: E731
+        self.S_rpn, self.S_rcnn = int(rpn_config["sampling"]["num_samples"]), int(rcnn_config["sampling"]["num_samples"])
+        self.scores_v, self.deltas_v = f32(B, Nv, 2), f32(B, Nv, 1, 4)
+        self.rois, self.roi_scores, self.roi_classes, self.num_valid = f32(B, R, 4), f32(B, R), i32(B, R), i32(B)
+        self.rois_abs = f32(B, R, 4)
+        self.rpn_tl, self.rpn_tb = f32(B, Nv, 2), f32(B, Nv, 1, 4)
+        self.rcnn_tl, self.rcnn_tb = f32(B, R, nc + 1), f32(B, R, nc, 4)
+        mk_s = lambda S, L: {"target_labels": f32(B, S, L), "pred_scores": f32(B, S, L), "target_boxes": f32(B, S, L - 1, 4),  # noqa: E731
+                             "pred_boxes": f32(B, S, L - 1, 4), "indices": torch.empty((B, S), dtype=torch.int64, device=dev),
+                             "counts": i32(B, 2), "losses": f32(3), "d_pred_scores": f32(B, S, L), "d_pred_boxes": f32(B, S, L - 1, 4)}
+        self.rpn_samples, self.rcnn_samples = mk_s(self.S_rpn, 2), mk_s(self.S_rcnn, nc + 1)
+        self.pooled = f32(B, R, self.P, self.P, C)
+        self.codes = torch.empty((B, R, self.P, self.P, C // 4), dtype=torch.uint8, device=dev)
+        self.d_feature = f32(B, self.Hf, self.Wf, C)
+        L_ = self._lib
+        ws = lambda n: (torch.empty(max(int(n), 16), dtype=torch.uint8, device=dev), int(n))  # noqa: E731
+        self.ws_post = ws(L_.frcnn_postprocess_workspace_bytes(B, Nv, 1, self.per_class, self.R))
+        self.ws_tgt_rpn = ws(L_.frcnn_generate_targets_workspace_bytes(B, Nv))
+        self.ws_tgt_rcnn = ws(L_.frcnn_generate_targets_workspace_bytes(B, R))
+        self.ws_smp_rpn = ws(L_.frcnn_sample_indices_workspace_bytes(B, Nv))
+        self.ws_smp_rcnn = ws(L_.frcnn_sample_indices_workspace_bytes(B, R))
+        self._step = 0
+
+    def algorithmic_bytes(self):
+        B, R, C, HW = self.B, self.R, self.C, self.Hf * self.Wf
+        bins = self.P * self.P * R
+        return {
+            "roi_pool_fwd_codes": B * (4 * C * (HW + bins) + bins * C // 4),
+            "roi_pool_bwd": B * (4 * C * (bins + 2 * HW) + bins * C // 4),
+            "match_rpn": 40 * self.Nv * B,
+        }
+
+    def _samples(self, tl, tb, N, L, cfg, pred_scores, pred_boxes, out, ws, seed):
+        check(self._lib.frcnn_sample_and_gather(ptr(tl), self.B, N, L, int(cfg["num_samples"]), float(cfg["foreground_proportion"]),
+                                                seed, ptr(out["indices"]), ptr(out["counts"]), ptr(pred_scores), ptr(tb),
+                                                ptr(pred_boxes), ptr(out["target_labels"]), ptr(out["pred_scores"]),
+                                                ptr(out["target_boxes"]), ptr(out["pred_boxes"]), ptr(ws[0]), ws[1], stream()),
+              "sample_and_gather")
+        rows = self.B * int(cfg["num_samples"])
+        check(self._lib.frcnn_sampled_losses(ptr(out["target_labels"]), ptr(out["pred_scores"]), rows, L, ptr(out["target_boxes"]),
+                                             ptr(out["pred_boxes"]), rows * (L - 1), 1.0, 1.0, ptr(out["losses"]),
+                                             ptr(out["d_pred_scores"]), ptr(out["d_pred_boxes"]), stream()), "sampled_losses")
+
+    def forward(self, pred_scores, pred_boxes, feature_maps, gt_labels, gt_boxes, rcnn_scores, rcnn_boxes, seed=None,
+                between=None):
+        """Everything up to and including the four losses.  pred_scores [B,N,2] / pred_boxes [B,N,1,4]: the RPN heads'
+        outputs over ALL anchors; rcnn_scores [B,R,nc+1] / rcnn_boxes [B,R,nc,4]: the Dense heads' outputs."""
+        L_, B, Nv, R, H, W = self._lib, self.B, self.Nv, self.R, float(self.image_shape[0]), float(self.image_shape[1])
+        seed = self._step if seed is None else int(seed)
+        self._step += 1
+        n_idx = self.valid_idx.numel()
+        check(L_.frcnn_gather_rows(ptr(pred_scores), B, self.N, 2, ptr(self.valid_idx), n_idx, ptr(self.scores_v), stream()), "gather_rows")
+        check(L_.frcnn_gather_rows(ptr(pred_boxes), B, self.N, 4, ptr(self.valid_idx), n_idx, ptr(self.deltas_v), stream()), "gather_rows")
+        nms = self.rpn["nms"]
+        check(L_.frcnn_postprocess(H, W, ptr(self.valid_anchors), 0, ptr(self.scores_v), ptr(self.deltas_v), B, Nv, 1,
+                                   float(nms["score_threshold"]), float(nms["iou_threshold"]), self.per_class, R,
+                                   self.pre_nms_top_n, ptr(self.rois), ptr(self.roi_scores), ptr(self.roi_classes),
+                                   ptr(self.num_valid), None, None, ptr(self.ws_post[0]), self.ws_post[1], stream()),
+              "postprocess_output")
+        sm = self.rpn["sampling"]
+        (fl, fh), (bl, bh) = sm["foreground_iou_interval"], sm["background_iou_interval"]
+        check(L_.frcnn_generate_targets_objectness(ptr(gt_labels), ptr(gt_boxes), B, self.G, self.nc + 1, ptr(self.valid_anchors),
+                                                   0, Nv, H, W, float(fl), float(fh), float(bl), float(bh), ptr(self.rpn_tl),
+                                                   ptr(self.rpn_tb), None, None, ptr(self.ws_tgt_rpn[0]), self.ws_tgt_rpn[1],
+                                                   stream()), "generate_targets")
+        self._samples(self.rpn_tl, self.rpn_tb, Nv, 2, sm, self.scores_v, self.deltas_v, self.rpn_samples, self.ws_smp_rpn,
+                      2 * seed)
+        check(L_.frcnn_roi_pool_forward_argmax(ptr(feature_maps), B, self.Hf, self.Wf, self.C, ptr(self.rois), R, self.P, self.k,
+                                               ptr(self.pooled), ptr(self.codes), stream()), "roi_pool_forward_argmax")
+        if between is not None:
+            between()  # e.g. the caller's Dense heads on self.pooled producing rcnn_scores / rcnn_boxes
+        check(L_.frcnn_scale_boxes(ptr(self.rois), B * R, H, W, 0, ptr(self.rois_abs), stream()), "to_absolute")
+        sm = self.rcnn["sampling"]
+        (fl, fh), (bl, bh) = sm["foreground_iou_interval"], sm["background_iou_interval"]
+        check(L_.frcnn_generate_targets(ptr(gt_labels), ptr(gt_boxes), B, self.G, self.nc, ptr(self.rois_abs), 1, R, H, W,
+                                        float(fl), float(fh), float(bl), float(bh), ptr(self.rcnn_tl), ptr(self.rcnn_tb), None,
+                                        None, ptr(self.ws_tgt_rcnn[0]), self.ws_tgt_rcnn[1], stream()), "generate_targets")
+        self._samples(self.rcnn_tl, self.rcnn_tb, R, self.nc + 1, sm, rcnn_scores, rcnn_boxes, self.rcnn_samples,
+                      self.ws_smp_rcnn, 2 * seed + 1)
+        return self.rpn_samples["losses"], self.rcnn_samples["losses"]
+
+    def backward(self, d_pooled):
+        """dL/d(pooled) [B,R,P,P,C] -> dL/d(feature_maps) from the saved arg-max codes."""
+        check(self._lib.frcnn_roi_pool_backward_argmax(self.B, self.Hf, self.Wf, self.C, ptr(self.rois), self.R, self.P, self.k,
+                                                       ptr(d_pooled), ptr(self.codes), ptr(self.d_feature), stream()),
+              "roi_pool_backward_argmax")
+        return self.d_feature
+
+    def step(self, pred_scores, pred_boxes, feature_maps, gt_labels, gt_boxes, rcnn_scores, rcnn_boxes, d_pooled, seed=None,
+             between=None):
+        self.forward(pred_scores, pred_boxes, feature_maps, gt_labels, gt_boxes, rcnn_scores, rcnn_boxes, seed, between)
+        return self.backward(d_pooled)

@@ -6,6 +6,8 @@ from __future__ import annotations
 import torch
 
 from ..._tensor import as_device, check, lib, ptr, stream
+from ...utils.boxes import to_absolute
+from ...utils.training import get_training_samples as _get_training_samples
 
 
 def roi_pool_forward(feature_maps, rois, pooled_size, kernel_size):
@@ -111,3 +113,33 @@ class ROIPooling:
         return pooled
 
     __call__ = call
+
+
+class FastRCNNDetector:
+    """The hot-path part of fast_rcnn_detector.py:7-130: RoI pooling, the relative -> absolute regions of ``call`` (:66)
+    and ``get_training_samples`` (:71-130).  The Dense heads stay with the caller (cuBLAS territory, out of scope):
+    ``pool`` returns what they consume, ``regions`` what ``call`` returns next to their outputs."""
+
+    def __init__(self, image_shape, num_classes, config, name="fast_rcnn_detector"):
+        self._image_shape = image_shape
+        self.num_classes = int(num_classes)
+        self.name = name
+        self._roi_pooling = ROIPooling(name="regions_of_interest_pooling", **config["roi_pooling"])  # :23
+
+    def pool(self, feature_maps, rois):
+        """:60 ``self._roi_pooling(feature_maps, rois, True, True)`` -> [B,R,P*P*C] (differentiable w.r.t. feature_maps)."""
+        return self._roi_pooling(feature_maps, rois, True, True)
+
+    def regions(self, rois):
+        """:66 ``to_absolute(rois, self._image_shape)``."""
+        return to_absolute(rois, self._image_shape)
+
+    def get_training_samples(self, gt_labels, gt_boxes, regions, pred_scores, pred_boxes, foreground_iou_interval,
+                             background_iou_interval, num_samples, foreground_proportion, **sampler):
+        """FastRCNNDetector.get_training_samples, fast_rcnn_detector.py:71-130 -- same signature, called as
+        ``get_training_samples(gt_labels, gt_boxes, **rcnn_output, **config["rcnn"]["sampling"])``
+        (models/faster_rcnn.py:82-84).  regions [B,R,4] abs, pred_scores [B,R,nc+1], pred_boxes [B,R,nc,4] ->
+        {"target_labels", "pred_scores": [B,S,nc+1]; "target_boxes", "pred_boxes": [B,S,nc,4]}."""
+        return _get_training_samples(gt_labels, gt_boxes, regions, pred_scores, pred_boxes, self._image_shape,
+                                     foreground_iou_interval, background_iou_interval, num_samples, foreground_proportion,
+                                     objectness=False, **sampler)

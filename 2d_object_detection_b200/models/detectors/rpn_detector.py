@@ -13,6 +13,7 @@ import torch
 
 from ..._tensor import as_device, check, lib, ptr, require_cuda, stream
 from ...utils.boxes import clip_to_window
+from ...utils.training import get_training_samples as _get_training_samples
 
 
 def generate_anchors(grid_shape, scales, aspect_ratios, base_anchor_shape, stride_shape=(16, 16)):
@@ -67,11 +68,23 @@ class RPNAnchors:
         image_height, image_width = image_shape[0], image_shape[1]
         self._clipped = clip_to_window(self._anchors, [0, 0, image_width, image_height])  # :93-94
         self._valid_idx = valid_anchor_indices(self._anchors, image_shape)                 # :216-224
-        self._valid_anchors = self._anchors[self._valid_idx].contiguous()
+        self._valid_anchors = _gather_rows(self._anchors[None], self._valid_idx)[0]               # :226
 
     @property
     def anchors(self):
         return self._anchors
+
+    def get_training_samples(self, gt_labels, gt_boxes, regions, pred_scores, pred_boxes, foreground_iou_interval,
+                             background_iou_interval, num_samples, foreground_proportion, **sampler):
+        """RPNDetector.get_training_samples, rpn_detector.py:98-160 -- same signature, called as
+        ``get_training_samples(gt_labels, gt_boxes, **rpn_output, **config["rpn"]["sampling"])`` (models/faster_rcnn.py:77-79).
+        gt_labels [B,G,nc+1], gt_boxes [B,G,4] rel, regions [N,4] abs, pred_scores [B,N,2], pred_boxes [B,N,1,4] ->
+        {"target_labels", "pred_scores": [B,S,2]; "target_boxes", "pred_boxes": [B,S,1,4]}.  The objectness one-hot (:141)
+        is folded into the matching kernels.  ``sampler``: generator= / seed= / check_background= (the reference draws from
+        TF's unseeded generator)."""
+        return _get_training_samples(gt_labels, gt_boxes, regions, pred_scores, pred_boxes, self._image_shape,
+                                     foreground_iou_interval, background_iou_interval, num_samples, foreground_proportion,
+                                     objectness=True, **sampler)
 
     def __call__(self, pred_scores, pred_boxes_encoded, training=False):
         """The tail of RPNDetector.call (rpn_detector.py:88-96) given the conv heads' outputs."""
@@ -80,3 +93,6 @@ class RPNAnchors:
                     "pred_boxes": _gather_rows(pred_boxes_encoded, self._valid_idx)}
         return {"regions": self._clipped, "pred_scores": as_device(pred_scores),
                 "pred_boxes": as_device(pred_boxes_encoded)}
+
+
+RPNDetector = RPNAnchors  # the reference's class name; the conv heads stay with the caller (out of scope)

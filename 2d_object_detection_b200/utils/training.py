@@ -12,14 +12,17 @@ from .._tensor import as_device, check, lib, ptr, stream, workspace
 
 
 def generate_targets_batched(gt_labels, gt_boxes, regions, image_shape, foreground_iou_interval,
-                             background_iou_interval, return_extra=False):
+                             background_iou_interval, return_extra=False, objectness=False):
     """Batched utils/training.py:7-77.  gt_labels [B,G,nc+1]; gt_boxes [B,G,4] rel; regions [N,4] or [B,N,4] abs.
 
-    Returns (target_labels [B,N,nc+1], target_boxes_encoded [B,N,nc,4]) (+ max_iou [B,N], argmax [B,N] int32)."""
+    Returns (target_labels [B,N,nc+1], target_boxes_encoded [B,N,nc,4]) (+ max_iou [B,N], argmax [B,N] int32).
+    ``objectness=True`` is the RPN's call (rpn_detector.py:141-149): the labels generate_targets sees are
+    one_hot(int(sum(gt_labels, -1)), 2), computed inside the matching kernels; outputs are [B,N,2] / [B,N,1,4]."""
     gl, gb, reg = as_device(gt_labels), as_device(gt_boxes), as_device(regions)
     if gl.dim() != 3 or gb.dim() != 3 or gb.shape[-1] != 4 or gl.shape[:2] != gb.shape[:2]:
         raise ValueError(f"gt_labels [B,G,nc+1] / gt_boxes [B,G,4] expected, got {tuple(gl.shape)} / {tuple(gb.shape)}")
-    B, G, L = gl.shape
+    B, G, Lin = gl.shape
+    L = 2 if objectness else Lin
     nc = L - 1
     batched = reg.dim() == 3
     N = reg.shape[-2]
@@ -34,9 +37,10 @@ def generate_targets_batched(gt_labels, gt_boxes, regions, image_shape, foregrou
     ws_bytes = Lb.frcnn_generate_targets_workspace_bytes(B, N)
     ws = workspace(ws_bytes)
     (fl, fh), (bl, bh) = foreground_iou_interval, background_iou_interval
-    check(Lb.frcnn_generate_targets(ptr(gl), ptr(gb), B, G, nc, ptr(reg), int(batched), N, float(image_shape[0]),
-                                    float(image_shape[1]), float(fl), float(fh), float(bl), float(bh), ptr(tl),
-                                    ptr(tb), ptr(mi), ptr(am), ptr(ws), ws_bytes, stream()), "generate_targets")
+    fn = Lb.frcnn_generate_targets_objectness if objectness else Lb.frcnn_generate_targets
+    check(fn(ptr(gl), ptr(gb), B, G, Lin if objectness else nc, ptr(reg), int(batched), N, float(image_shape[0]),
+             float(image_shape[1]), float(fl), float(fh), float(bl), float(bh), ptr(tl), ptr(tb), ptr(mi), ptr(am), ptr(ws),
+             ws_bytes, stream()), "generate_targets")
     return (tl, tb, mi, am) if return_extra else (tl, tb)
 
 
@@ -52,9 +56,23 @@ def generate_targets(gt_labels, gt_boxes, regions, image_shape, foreground_iou_i
 def rpn_objectness_labels(gt_labels):
     """rpn_detector.py:141: one_hot(int(sum(gt_labels, -1)), depth=2); padded rows become [1, 0] (trap T11)."""
     gl = as_device(gt_labels)
-    s = gl.sum(-1).to(torch.int64)
-    inside = ((s >= 0) & (s <= 1)).unsqueeze(-1)
-    return torch.nn.functional.one_hot(s.clamp(0, 1), 2).to(torch.float32) * inside
+    out = torch.empty(tuple(gl.shape[:-1]) + (2,), dtype=torch.float32, device=gl.device)
+    check(lib().frcnn_objectness_labels(ptr(gl), out.numel() // 2, gl.shape[-1], ptr(out), stream()), "objectness_labels")
+    return out
+
+
+def get_training_samples(gt_labels, gt_boxes, regions, pred_scores, pred_boxes, image_shape, foreground_iou_interval,
+                         background_iou_interval, num_samples, foreground_proportion, objectness=False, generator=None,
+                         seed=None, check_background=True):
+    """The body both detectors share (rpn_detector.py:98-160 with ``objectness=True``, fast_rcnn_detector.py:71-130):
+    generate_targets per image -> get_sample_indices per image -> the four tf.gather(batch_dims=1).  Three kernel launches
+    (match, labels, sample + gather).  Returns the reference's dict: target_labels, pred_scores [B,S,nc+1];
+    target_boxes, pred_boxes [B,S,nc,4]."""
+    tl, tb = generate_targets_batched(gt_labels, gt_boxes, regions, image_shape, foreground_iou_interval,
+                                      background_iou_interval, objectness=objectness)
+    out = sample_and_gather_batched(tl, num_samples, foreground_proportion, pred_scores, tb, pred_boxes, generator=generator,
+                                    seed=seed, check_background=check_background)
+    return {k: out[k] for k in ("target_labels", "pred_scores", "target_boxes", "pred_boxes")}
 
 
 _seed_counter = [0]

@@ -147,7 +147,11 @@ FRCNN_API int frcnn_nms(const float* boxes, const float* scores, int segments, i
  * The reference configuration (pooled_size 7, kernel_size 2, C % 512 == 0) runs the row-streaming TMA kernel
  * (roi_pool_stream.cu); it builds CUtensorMap descriptors of feature_maps on the host (cached per pointer and shape,
  * cuTensorMapEncodeTiled through cudaGetDriverEntryPoint), so feature_maps must stay valid until the stream has run.
- * Other shapes run the bin-row walk / generic kernels (roi_pool.cu).  All variants give identical bits. */
+ * Other shapes run the bin-row walk / generic kernels (roi_pool.cu).  All variants give identical bits.
+ * PRECONDITION: feature_maps (and dy in the backward) hold FINITE values.  At an integer sample position TF reads
+ * ceil(in) == floor(in) for the right / bottom neighbour; the walk and streaming kernels read the pixel after it with
+ * weight exactly 0 -- (next - a) * 0 == 0 for finite data, NaN if that extra pixel is Inf / NaN
+ * (tests: test_roi_pool_integer_positions_read_one_pixel_further_finite_inputs). */
 FRCNN_API int frcnn_roi_pool_forward(const float* feature_maps, int B, int Hf, int Wf, int C, const float* rois, int R,
                            int pooled_size, int kernel_size, float* out, frcnn_stream_t stream);
 
@@ -186,6 +190,19 @@ FRCNN_API int frcnn_generate_targets(const float* gt_labels, const float* gt_box
                            float* max_iou, int32_t* argmax, void* workspace, size_t workspace_bytes,
                            frcnn_stream_t stream);
 
+/* The RPN's form (models/detectors/rpn_detector.py:141-149): the objectness labels
+ *   one_hot(cast(reduce_sum(gt_labels, -1), int32), depth=2)
+ * are computed inside the matching kernels from gt_labels [B,G,num_classes_plus_1], then generate_targets runs on them:
+ * target_labels [B,N,2], target_boxes [B,N,1,4].  Padding rows become [1, 0] and are NOT removed (trap T11), exactly as in
+ * the reference.  frcnn_objectness_labels writes those labels on their own ([rows,num_classes_plus_1] -> [rows,2]). */
+FRCNN_API int frcnn_generate_targets_objectness(const float* gt_labels, const float* gt_boxes, int B, int G,
+                                      int num_classes_plus_1, const float* regions, int regions_batched, int N,
+                                      float image_height, float image_width, float fg_lo, float fg_hi, float bg_lo,
+                                      float bg_hi, float* target_labels, float* target_boxes, float* max_iou,
+                                      int32_t* argmax, void* workspace, size_t workspace_bytes, frcnn_stream_t stream);
+FRCNN_API int frcnn_objectness_labels(const float* gt_labels, int64_t rows, int num_classes_plus_1, float* out,
+                            frcnn_stream_t stream);
+
 /* ---- utils/metrics.py:57-84 AveragePrecision.update_state_single_image, batched ------------------------------------
  *   gt_boxes [B,G,4] (rows summing to 0 = padding), pred_boxes [B,M,4]; true_positives [B,M] int32: 1 where the
  *   prediction is the highest-IoU prediction (first maximum) of at least one ground-truth box and that IoU exceeds
@@ -220,7 +237,7 @@ FRCNN_API int frcnn_sampled_losses(const float* target_labels, const float* pred
  *   target_labels / pred_scores, out_target_boxes / out_pred_boxes [B,num_samples,nc,4] from target_boxes / pred_boxes. */
 FRCNN_API size_t frcnn_sample_indices_workspace_bytes(int B, int N);
 FRCNN_API int frcnn_sample_and_gather(const float* target_labels, int B, int N, int num_classes_plus_1, int num_samples,
-                            float foreground_proportion, uint64_t seed, int64_t* indices, int32_t* counts,
+                            double foreground_proportion, uint64_t seed, int64_t* indices, int32_t* counts,
                             const float* pred_scores, const float* target_boxes, const float* pred_boxes,
                             float* out_labels, float* out_scores, float* out_target_boxes, float* out_pred_boxes,
                             void* workspace, size_t workspace_bytes, frcnn_stream_t stream);

@@ -172,6 +172,15 @@ def test_postprocess_rpn_form(det, orc, syn, wname, batch, top_n):
     assert (host(out["num_valid_detections"]) == 300).all()
 
 
+def test_postprocess_dense_b16_end_to_end(det, orc, syn):
+    """BASELINE configs[3] through the whole postprocess_output (decode + score keys + pre-NMS top 12000 + NMS + finalize,
+    R = 1000, N = 117,600 anchors/image), two images of the dense workload: kept-index sets bit-exact."""
+    w, anchors, scores, deltas, _ = _decoded(orc, syn, "dense_b16", 2, 20243)
+    assert w.num_anchors == 117600 and w.max_total_size == 1000 and w.pre_nms_top_n == 12000
+    out, ref = _check_post(det, orc, w.image_shape, anchors, scores, deltas, w.nms_kwargs(), w.pre_nms_top_n)
+    assert (host(out["num_valid_detections"]) > 300).all()
+
+
 def test_postprocess_decode_stage_and_unclipped_iou(det, orc, syn):
     w, anchors, scores, deltas, boxes = _decoded(orc, syn, "kitti_b8", 2, 5)
     brel, keys = det.decode_filter(w.image_shape, dev(anchors), dev(scores), dev(deltas), 0.0)
@@ -294,6 +303,29 @@ def test_roi_pool_forward_row_streaming_edge_cases(det, orc, syn, rng, grid, C):
     ref = orc.roi_pool_forward(f, rois, 7, 2)
     out = host(det.roi_pool_forward(dev(f), dev(rois), 7, 2))
     np.testing.assert_array_equal(out, ref)
+
+
+def test_roi_pool_integer_positions_read_one_pixel_further_finite_inputs(det, orc, rng):
+    """The streaming kernels read the right / bottom neighbour of a sample at lo + 1 with weight exactly 0 where TF reads
+    ceil(in) == lo (integer sample positions).  For FINITE maps -- the documented precondition of the RoI kernels
+    (include/frcnn_b200.h) -- (next - a) * 0 == (a - a) * 0 == 0, so results are bit-identical; this pins it on RoIs whose
+    every sample sits on an integer position, including the last column / row where lo + 1 is the next feature row, the
+    next image or the TMA zero fill.  (A non-finite neighbour would give NaN here and the sampled value in TF.)"""
+    Hf, Wf, C = 14, 27, 512
+    f = (rng.standard_normal((2, Hf, Wf, C)) * 1e30).astype(F)  # huge but finite neighbours
+    rois = np.zeros((2, 4, 4), F)
+    rois[:, 0] = [0.0, 0.0, 0.5, 1.0]                 # x samples on pixels 0, 1, ..., 13; y samples on rows 0 .. 13
+    rois[:, 1] = [0.5, 0.0, 1.0, 1.0]                 # x samples on pixels 13 .. 26: the last one is the last column
+    rois[:, 2] = [1.0, 1.0, 1.0, 1.0]                 # every sample on the last pixel of the map
+    rois[:, 3] = [13 / 26, 0.0, 13 / 26, 1.0]         # one integer column
+    ref = orc.roi_pool_forward(f, rois, 7, 2)
+    np.testing.assert_array_equal(host(det.roi_pool_forward(dev(f), dev(rois), 7, 2)), ref)
+    out, codes = det.roi_pool_forward_argmax(dev(f), dev(rois), 7, 2)
+    np.testing.assert_array_equal(host(out), ref)
+    dy = rng.standard_normal(ref.shape).astype(F)
+    g = host(det.roi_pool_backward_argmax(f.shape, dev(rois), dev(dy), codes, 7, 2))
+    gref = orc.roi_pool_backward(f, rois, dy, 7, 2)
+    np.testing.assert_allclose(g, gref, rtol=1e-5, atol=1e-5 * np.abs(gref).max())
 
 
 def test_roi_pool_other_window_sizes_and_out_of_range(det, orc, syn, rng):
@@ -674,3 +706,156 @@ def test_average_precision_matching_and_metric(det, rng):
             total += n
         want.append(ref.average_precision(np.concatenate(tps), sc.reshape(-1), total))
     np.testing.assert_allclose(float(m.result()), float(np.mean(want)), rtol=1e-5)
+
+
+# ------------------------------------------------------------------ training boundary: get_training_samples + TrainStepEngine
+def test_objectness_folded_into_matching_equals_two_step(det, orc, syn, rng):
+    """rpn_detector.py:141 folded into the matching kernels == the explicit one-hot followed by generate_targets, and both
+    == the oracle (padding rows become [1, 0] and stay in the gt list, T11); odd label sums (2 -> [0, 0]) included."""
+    w = syn.WORKLOADS["kitti_b8"]
+    anchors = orc.generate_anchors(w.grid, w.scales, w.aspect_ratios, w.base_anchor_shape)
+    regions = anchors[orc.valid_anchor_indices(anchors, w.image_shape)]
+    gl, gb = syn.ground_truth(rng, 4)
+    gl[0, 1, 3] = 1.0  # a row with two hot entries: objectness index 2 -> [0, 0] -> removed as padding
+    obj = orc.rpn_objectness_labels(gl)
+    tl, tb = det.generate_targets_batched(dev(gl), dev(gb), dev(regions), w.image_shape, [0.7, 1.0], [0.0, 0.3], objectness=True)
+    tl2, tb2 = det.generate_targets_batched(det.rpn_objectness_labels(dev(gl)), dev(gb), dev(regions), w.image_shape,
+                                            [0.7, 1.0], [0.0, 0.3])
+    assert torch.equal(tl, tl2) and torch.equal(tb, tb2)
+    rl, rb = orc.generate_targets_batched(obj, gb, regions, w.image_shape, [0.7, 1.0], [0.0, 0.3])
+    np.testing.assert_array_equal(host(tl), rl)
+    np.testing.assert_allclose(host(tb), rb, rtol=RTOL, atol=1e-6)
+
+
+def test_get_training_samples_reference_signature(det, orc, syn, rng):
+    """RPNDetector.get_training_samples / FastRCNNDetector.get_training_samples called the way models/faster_rcnn.py:77-84
+    calls them (**detector_output, **config["sampling"]): shapes, the sampling rule, and every sampled row equal to the row
+    the oracle's targets hold at the sampled index (the draw itself is random in the reference)."""
+    cfg = syn.REFERENCE_CONFIG
+    w = syn.WORKLOADS["kitti_b8_ref12"]
+    B, R, nc = 3, 300, cfg["num_classes"]
+    rpn = det.RPNDetector(w.image_shape, (None,) + tuple(w.grid) + (1024,), cfg["rpn"])
+    scores, deltas = syn.rpn_head_outputs(rng, B, w.num_anchors)
+    gl, gb = syn.ground_truth(rng, B)
+    rpn_output = rpn(dev(scores), dev(deltas), training=True)
+    smp = rpn.get_training_samples(dev(gl), dev(gb), **rpn_output, **cfg["rpn"]["sampling"], seed=5)
+    S = cfg["rpn"]["sampling"]["num_samples"]
+    assert {k: tuple(v.shape) for k, v in smp.items()} == {"target_labels": (B, S, 2), "pred_scores": (B, S, 2),
+                                                          "target_boxes": (B, S, 1, 4), "pred_boxes": (B, S, 1, 4)}
+    regions = host(rpn_output["regions"])
+    rl, rb = orc.generate_targets_batched(orc.rpn_objectness_labels(gl), gb, regions, w.image_shape, [0.7, 1.0], [0.0, 0.3])
+    sc_v, dl_v = host(rpn_output["pred_scores"]), host(rpn_output["pred_boxes"])
+    tl, ps, tb, pb = (host(smp[k]) for k in ("target_labels", "pred_scores", "target_boxes", "pred_boxes"))
+    for b in range(B):
+        # every sampled (target, prediction) row is a row of the full tensors at ONE common index (the four gathers agree)
+        rows = {tuple(np.concatenate([rl[b, i], sc_v[b, i], dl_v[b, i].ravel()]).tolist()) for i in range(regions.shape[0])}
+        for s in range(S):
+            assert tuple(np.concatenate([tl[b, s], ps[b, s], pb[b, s].ravel()]).tolist()) in rows
+        n_fg = int((tl[b, :, 1] == 1).sum())
+        assert n_fg <= S // 2 and (tl[b, :n_fg, 1] == 1).all() and (tl[b, n_fg:, 0] == 1).all()  # foregrounds first
+        fg_rows = np.nonzero(tl[b, :, 1] == 1)[0]
+        assert (np.abs(tb[b, fg_rows]).sum((-1, -2)) > 0).all() and (tb[b, n_fg:] == 0).all()
+    # Fast R-CNN form: batched regions, 7 classes
+    rcnn = det.FastRCNNDetector(w.image_shape, nc, cfg["rcnn"])
+    rois = syn.random_rois(rng, B, R)
+    rois[:, :20] = gb[:, :20]  # some RoIs on the ground truth: real foregrounds
+    lg = rng.normal(0, 1, (B, R, nc + 1)).astype(F)
+    ps7 = (np.exp(lg) / np.exp(lg).sum(-1, keepdims=True)).astype(F)
+    dl7 = rng.normal(0, 0.1, (B, R, nc, 4)).astype(F)
+    rcnn_output = {"regions": rcnn.regions(dev(rois)), "pred_scores": dev(ps7), "pred_boxes": dev(dl7)}
+    np.testing.assert_array_equal(host(rcnn_output["regions"]), orc.to_absolute(rois, w.image_shape))
+    smp = rcnn.get_training_samples(dev(gl), dev(gb), **rcnn_output, **cfg["rcnn"]["sampling"], seed=6)
+    S = cfg["rcnn"]["sampling"]["num_samples"]
+    assert tuple(smp["target_labels"].shape) == (B, S, nc + 1) and tuple(smp["pred_boxes"].shape) == (B, S, nc, 4)
+    rl, rb = orc.generate_targets_batched(gl, gb, orc.to_absolute(rois, w.image_shape), w.image_shape, [0.5, 1.0], [0.0, 0.5])
+    tl, ps, tb, pb = (host(smp[k]) for k in ("target_labels", "pred_scores", "target_boxes", "pred_boxes"))
+    for b in range(B):
+        for s in range(S):
+            hit = np.nonzero((rl[b] == tl[b, s]).all(-1) & (ps7[b] == ps[b, s]).all(-1) & (dl7[b] == pb[b, s]).all((-1, -2)))[0]
+            assert hit.size >= 1
+            np.testing.assert_allclose(tb[b, s], rb[b, hit[0]], rtol=RTOL, atol=1e-6)
+        n_fg = int((tl[b, :, 0] == 0).sum())
+        assert 1 <= n_fg <= 16 and (tl[b, :n_fg, 0] == 0).all() and (tl[b, n_fg:, 0] == 1).all()
+    pooled = rcnn.pool(dev(syn.feature_maps(rng, B, w.grid, 512)), dev(rois))
+    assert tuple(pooled.shape) == (B, R, 49 * 512)
+
+
+def test_sampling_quota_limits_are_rejected_not_hung(det, rng):
+    """a foreground quota >= 4096 (the sort buffer) used to spin forever; the C ABI now refuses it, together with
+    proportions outside [0, 1]; a quota just under the limit with more than 4096 foregrounds works (chunked selection)."""
+    N = 9000
+    tl = np.zeros((1, N, 2), F)
+    tl[0, :6000, 1] = 1.0  # 6000 foregrounds
+    tl[0, 6000:, 0] = 1.0
+    with pytest.raises(ValueError):
+        det.sample_and_gather_batched(dev(tl), 8192, 0.5, seed=1)      # quota 4096
+    with pytest.raises(ValueError):
+        det.sample_and_gather_batched(dev(tl), 64, 1.5, seed=1)
+    out = det.sample_and_gather_batched(dev(tl), 8190, 0.5, seed=1)    # quota 4095 < 4096, 6000 candidates: two chunks
+    idx = host(out["indices"])[0]
+    assert len(set(idx[:4095].tolist())) == 4095 and (idx[:4095] < 6000).all() and (idx[4095:] >= 6000).all()
+    # tf.math.round(num_samples * proportion) on the Python double, half to even: 10 * 0.35 = 3.5 -> 4 (float32 0.35 gave 3)
+    tl2 = np.zeros((1, 40, 2), F)
+    tl2[0, :20, 1] = 1.0
+    tl2[0, 20:, 0] = 1.0
+    out = det.sample_and_gather_batched(dev(tl2), 10, 0.35, seed=2)
+    assert int((host(out["target_labels"])[0, :, 1] == 1).sum()) == 4
+
+
+def test_train_step_engine_matches_composed_calls_and_is_graph_capturable(det, orc, syn, rng):
+    """TrainStepEngine (pre-allocated, C-ABI calls only) == the same step composed from the public functions, and a CUDA
+    graph of the step replays to the same bits (proposals, samples, losses, pooled features, arg-max codes, dFeature)."""
+    cfg = syn.REFERENCE_CONFIG
+    w = syn.WORKLOADS["kitti_b8"]
+    B, C, nc = 2, 512, cfg["num_classes"]
+    rpn_cfg = {"nms": dict(cfg["rpn"]["nms"]), "sampling": cfg["rpn"]["sampling"]}
+    anchors = det.generate_anchors(w.grid, w.scales, w.aspect_ratios, w.base_anchor_shape)
+    eng = det.engine.TrainStepEngine(w.image_shape, B, w.grid, C, anchors, nc, rpn_cfg, cfg["rcnn"])
+    R = eng.R
+    scores, deltas = syn.rpn_head_outputs(rng, B, w.num_anchors)
+    gl, gb = syn.ground_truth(rng, B)
+    f = syn.feature_maps(rng, B, w.grid, C)
+    lg = rng.normal(0, 1, (B, R, nc + 1)).astype(F)
+    ps7 = (np.exp(lg) / np.exp(lg).sum(-1, keepdims=True)).astype(F)
+    dl7 = rng.normal(0, 0.1, (B, R, nc, 4)).astype(F)
+    dy = rng.standard_normal((B, R, 7, 7, C)).astype(F)
+    args = [dev(x) for x in (scores, deltas, f, gl, gb, ps7, dl7, dy)]
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        eng.step(*args, seed=11)
+    torch.cuda.synchronize()
+    # the same step from the public functions
+    vidx = det.valid_anchor_indices(anchors, w.image_shape)
+    va, sc_v, dl_v = det.remove_invalid_anchors_and_predictions(anchors, w.image_shape, args[0], args[1], vidx)
+    out = det.postprocess_output(w.image_shape, va, sc_v, dl_v, **rpn_cfg["nms"])
+    assert torch.equal(out["pred_boxes"], eng.rois) and torch.equal(out["num_valid_detections"], eng.num_valid)
+    smp = det.get_training_samples(args[3], args[4], va, sc_v, dl_v, w.image_shape, **rpn_cfg["sampling"], objectness=True,
+                                   seed=22, check_background=False)
+    for k in ("target_labels", "pred_scores", "target_boxes", "pred_boxes"):
+        assert torch.equal(smp[k], eng.rpn_samples[k]), k
+    l_cls, l_reg = det.sampled_losses(smp["target_labels"], smp["pred_scores"], smp["target_boxes"], smp["pred_boxes"])
+    assert l_cls.item() == eng.rpn_samples["losses"][0].item() and l_reg.item() == eng.rpn_samples["losses"][1].item()
+    pooled, codes = det.roi_pool_forward_argmax(args[2], eng.rois, 7, 2)
+    assert torch.equal(pooled, eng.pooled) and torch.equal(codes, eng.codes)
+    smp7 = det.get_training_samples(args[3], args[4], det.to_absolute(eng.rois, w.image_shape), args[5], args[6], w.image_shape,
+                                    **cfg["rcnn"]["sampling"], seed=23, check_background=False)
+    for k in ("target_labels", "pred_scores", "target_boxes", "pred_boxes"):
+        assert torch.equal(smp7[k], eng.rcnn_samples[k]), k
+    g_ref = det.roi_pool_backward_argmax(tuple(args[2].shape), eng.rois, args[7], codes, 7, 2)
+    assert torch.equal(g_ref, eng.d_feature)
+    ref_g = orc.roi_pool_backward(f, host(eng.rois), dy, 7, 2)
+    np.testing.assert_allclose(host(eng.d_feature), ref_g, rtol=RTOL, atol=RTOL * np.abs(ref_g).max())
+    eager = {k: v.clone() for k, v in (("rois", eng.rois), ("pooled", eng.pooled), ("codes", eng.codes), ("dfeat", eng.d_feature),
+                                       ("rpn_losses", eng.rpn_samples["losses"]), ("rcnn_losses", eng.rcnn_samples["losses"]))}
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        eng.step(*args, seed=11)
+    eng.d_feature.zero_()
+    eng.pooled.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    for k, v in (("rois", eng.rois), ("pooled", eng.pooled), ("codes", eng.codes), ("rpn_losses", eng.rpn_samples["losses"]),
+                 ("rcnn_losses", eng.rcnn_samples["losses"])):
+        assert torch.equal(v, eager[k]), k
+    # dFeature: TMA reduce-adds arrive in a different order on every run -> equal to rounding only
+    assert float((eng.d_feature - eager["dfeat"]).abs().max()) <= 2e-5 * float(eager["dfeat"].abs().max())
