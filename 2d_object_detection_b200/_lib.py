@@ -43,10 +43,11 @@ SIGNATURES = {
     "frcnn_decode_filter": (_i, [_f, _f, _p, _i, _p, _p, _i, _i, _i, _f, _p, _p, _p]),
     "frcnn_nms_workspace_bytes": (_sz, [_i, _i]),
     "frcnn_nms": (_i, [_p, _p, _i, _i, _f, _f, _i, _i, _p, _p, _p, _p, _sz, _p]),
-    "frcnn_roi_pool_forward": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _i, _p, _p]),
+    "frcnn_roi_pool_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "frcnn_roi_pool_forward": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _i, _p, _p, _sz, _p]),
     "frcnn_roi_pool_backward": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _i, _p, _p, _p]),
     "frcnn_roi_pool_argmax_supported": (_i, [_i, _i, _i]),
-    "frcnn_roi_pool_forward_argmax": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _i, _p, _p, _p]),
+    "frcnn_roi_pool_forward_argmax": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _i, _p, _p, _p, _sz, _p]),
     "frcnn_roi_pool_backward_argmax": (_i, [_i, _i, _i, _i, _p, _i, _i, _i, _p, _p, _p, _p]),
     "frcnn_generate_targets_workspace_bytes": (_sz, [_i, _i]),
     "frcnn_generate_targets": (_i, [_p, _p, _i, _i, _i, _p, _i, _i, _f, _f, _f, _f, _f, _f, _p, _p, _p, _p, _p, _sz,
@@ -61,6 +62,8 @@ SIGNATURES = {
     "frcnn_pipeline_create": (_i, [C.POINTER(_p), _i, _i, _i, _i, _i, _i, _i, _i]),
     "frcnn_pipeline_destroy": (None, [_p]),
     "frcnn_pipeline_run": (_i, [_p, _f, _f, _p, _p, _p, _p, _f, _f, _i, _p, _p, _p, _p]),
+    "frcnn_pipeline_submit": (_i, [_p, _f, _f, _p, _p, _p, _p, _f, _f, _i, _p, _p, _p, _p, C.POINTER(C.c_int32)]),
+    "frcnn_pipeline_wait": (_i, [_p, C.c_int32]),
 }
 
 _lib = None

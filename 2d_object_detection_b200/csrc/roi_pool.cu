@@ -19,6 +19,12 @@ constexpr bool kForceBinRowWalk = true;
 #else
 constexpr bool kForceBinRowWalk = false;
 #endif
+// FRCNN_DEFINES=FRCNN_AB_LEGACY_STREAM_FWD: the round-1 per-CTA streaming forward instead of the persistent one (A/B only).
+#ifdef FRCNN_AB_LEGACY_STREAM_FWD
+constexpr bool kLegacyStreamForward = true;
+#else
+constexpr bool kLegacyStreamForward = false;
+#endif
 
 // ---- tiny vector abstraction: float4 (C % 4 == 0) or float -------------------------------------
 __device__ __forceinline__ float4 vload(const float4* p) { return __ldg(p); }
@@ -768,8 +774,13 @@ using namespace frcnn;
 
 extern "C" {
 
+size_t frcnn_roi_pool_workspace_bytes(int B, int R, int C, int P, int k) {
+    if (B <= 0 || R <= 0 || !roi_pool_stream_supported(C, P, k) || kForceBinRowWalk) return 0;
+    return roi_pool_stream_workspace_bytes(B, R);
+}
+
 int frcnn_roi_pool_forward(const float* feat, int B, int Hf, int Wf, int C, const float* rois, int R, int P, int k,
-                           float* out, frcnn_stream_t stream) {
+                           float* out, void* workspace, size_t workspace_bytes, frcnn_stream_t stream) {
     FRCNN_REQUIRE(B > 0 && Hf > 0 && Wf > 0 && C > 0 && R >= 0 && P > 0 && k > 0, FRCNN_EINVAL,
                   "roi_pool_forward: bad shape");
     FRCNN_REQUIRE(P * k <= kMaxCrop, FRCNN_ELIMIT, "roi_pool_forward: pooled_size*kernel_size = %d > %d", P * k, kMaxCrop);
@@ -779,7 +790,10 @@ int frcnn_roi_pool_forward(const float* feat, int B, int Hf, int Wf, int C, cons
     if (R == 0) return 0;
     const dim3 grid(R, B);
     if (roi_pool_stream_supported(C, P, k) && !kForceBinRowWalk)
-        return launch_roi_pool_fwd_stream(feat, B, Hf, Wf, C, rois, R, out, nullptr, as_stream(stream));
+        return kLegacyStreamForward
+                   ? launch_roi_pool_fwd_stream(feat, B, Hf, Wf, C, rois, R, out, nullptr, as_stream(stream))
+                   : launch_roi_pool_fwd_persist(feat, B, Hf, Wf, C, rois, R, out, nullptr, workspace, workspace_bytes,
+                                                 as_stream(stream));
     if (C % 4 == 0 && k == 2 && (int64_t)Hf * Wf * (C / 4) < (1ll << 31)) {
         const int cv = C / 4;
         if (cv % 256 == 0)
@@ -839,7 +853,8 @@ int frcnn_roi_pool_argmax_supported(int C, int pooled_size, int kernel_size) {
 }
 
 int frcnn_roi_pool_forward_argmax(const float* feat, int B, int Hf, int Wf, int C, const float* rois, int R, int P, int k,
-                                  float* out, unsigned char* argmax_codes, frcnn_stream_t stream) {
+                                  float* out, unsigned char* argmax_codes, void* workspace, size_t workspace_bytes,
+                                  frcnn_stream_t stream) {
     FRCNN_REQUIRE(B > 0 && Hf > 0 && Wf > 0 && C > 0 && R >= 0 && B <= 65535, FRCNN_EINVAL, "roi_pool_forward_argmax: bad shape");
     FRCNN_REQUIRE(frcnn_roi_pool_argmax_supported(C, P, k) && (int64_t)Hf * Wf * (C / 4) < (1ll << 31), FRCNN_ELIMIT,
                   "roi_pool_forward_argmax: needs C %% 4 == 0, kernel_size == 2, pooled_size <= 8");
@@ -847,7 +862,10 @@ int frcnn_roi_pool_forward_argmax(const float* feat, int B, int Hf, int Wf, int 
                   "roi_pool_forward_argmax: pointers must be 16-byte aligned");
     if (R == 0) return 0;
     if (roi_pool_stream_supported(C, P, k) && !kForceBinRowWalk)
-        return launch_roi_pool_fwd_stream(feat, B, Hf, Wf, C, rois, R, out, argmax_codes, as_stream(stream));
+        return kLegacyStreamForward
+                   ? launch_roi_pool_fwd_stream(feat, B, Hf, Wf, C, rois, R, out, argmax_codes, as_stream(stream))
+                   : launch_roi_pool_fwd_persist(feat, B, Hf, Wf, C, rois, R, out, argmax_codes, workspace, workspace_bytes,
+                                                 as_stream(stream));
     return launch_codes<0>(feat, B, Hf, Wf, C, rois, R, P, out, argmax_codes, nullptr, nullptr, as_stream(stream));
 }
 

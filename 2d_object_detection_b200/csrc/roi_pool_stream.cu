@@ -22,6 +22,7 @@
 // RoIs whose x-samples span more than 51 feature columns do not fit the ring; they take a plain gather path.
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <stddef.h>
 
 #include "roi_axis.cuh"
 
@@ -150,6 +151,18 @@ __device__ __forceinline__ u64 lerp2(u64 a, u64 b, u64 ww, u64 one) {
     return d;
 }
 
+// The same with a sub that the compiler may not hoist or share: in the walk two or three consecutive crop rows often sit
+// between the same pair of feature rows, and hoisting the 14 packed differences (b - a) out of the crop-row loop keeps
+// 28 more registers alive across it -- exactly the registers the walk state needs.  Recomputing them costs a few percent
+// more packed adds and removes the spills.
+__device__ __forceinline__ u64 lerp2_nohoist(u64 a, u64 b, u64 ww, u64 one) {
+    u64 d;
+    asm volatile("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(b), "l"(a));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(d), "l"(ww));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(d), "l"(one), "l"(a));
+    return d;
+}
+
 // One crop_and_resize sampling position along an axis, in registers; op order of crop_and_resize_op.cc (= axis_sample).
 struct Sample {
     int lo, hi;
@@ -267,14 +280,15 @@ __device__ __forceinline__ unsigned codes_from_flags(unsigned a, unsigned b) {
 
 // Fold one finished crop row (top / bottom feature rows T / Bm, weight yl) into the 7 running bin maxima.  kFirst: first
 // crop row of the bin-row.  kCodes: also track which of the four window samples holds the maximum (training forward).
-template <bool kFirst, bool kCodes>
+template <bool kFirst, bool kCodes, bool kNoHoist = false>
 __device__ __forceinline__ void crop_row(const u64 (&T)[kS], const u64 (&Bm)[kS], float yl, u64 one, float2 (&M)[kP],
                                          unsigned& ca, unsigned& cb) {
     const u64 ww = pack2(yl, yl);
 #pragma unroll
     for (int j = 0; j < kP; ++j) {
-        const float2 v0 = unpack2(lerp2(T[2 * j], Bm[2 * j], ww, one));
-        const float2 v1 = unpack2(lerp2(T[2 * j + 1], Bm[2 * j + 1], ww, one));
+        const float2 v0 = unpack2(kNoHoist ? lerp2_nohoist(T[2 * j], Bm[2 * j], ww, one) : lerp2(T[2 * j], Bm[2 * j], ww, one));
+        const float2 v1 = unpack2(kNoHoist ? lerp2_nohoist(T[2 * j + 1], Bm[2 * j + 1], ww, one)
+                                           : lerp2(T[2 * j + 1], Bm[2 * j + 1], ww, one));
         if (kCodes) {
             if (kFirst) {
                 M[j] = v0;  // window position 0; the flags were cleared for this bin-row
@@ -540,6 +554,8 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads)
     for (int i = 0; i < n_after; ++i) emit(X0, X1, true);
 }
 
+
+#include "roi_pool_persist.cuh"
 
 // ================================================================================================
 // Backward from saved arg-max codes: the mirror image of the walk above (models/faster_rcnn.py:73,103 differentiates
@@ -1080,6 +1096,54 @@ int launch_roi_pool_fwd_stream(const float* feat, int B, int Hf, int Wf, int C, 
         else roi_pool_fwd_stream_kernel<0, false><<<grid, kThreads, smem, st>>>(*maps, feat, Hf, Wf, C, r4, R, nchunk, out, nullptr);
     }
     FRCNN_LAUNCH_CHECK("roi_pool_fwd_stream_kernel");
+    return 0;
+}
+
+size_t roi_pool_stream_workspace_bytes(int B, int R) { return 256 + (size_t)kRecStride * (size_t)B * (size_t)R; }
+
+// Persistent forward: records pre-kernel + warp-persistent pooling kernel.  workspace: [counter | records].
+int launch_roi_pool_fwd_persist(const float* feat, int B, int Hf, int Wf, int C, const float* rois, int R, float* out,
+                                unsigned char* codes, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    FRCNN_REQUIRE(workspace && workspace_bytes >= roi_pool_stream_workspace_bytes(B, R) && aligned16(workspace), FRCNN_EWORKSPACE,
+                  "roi_pool_forward: workspace too small (frcnn_roi_pool_workspace_bytes)");
+    FRCNN_REQUIRE(Hf <= 65535 && Wf <= 65535, FRCNN_ELIMIT, "roi_pool_forward: feature map side beyond 65535");
+    FRCNN_REQUIRE((int64_t)B * Hf * Wf < (1ll << 31) && (int64_t)B * R * (C / kWarpCh) < (1ll << 30), FRCNN_ELIMIT,
+                  "roi_pool_forward: tensor too large");
+    const size_t smem = (size_t)kWarps * kPWarpBytes;
+    int dev = 0;
+    FRCNN_CUDA(cudaGetDevice(&dev));
+    static bool configured[64] = {};
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        FRCNN_CUDA(cudaFuncSetAttribute(roi_pool_fwd_persist_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FRCNN_CUDA(cudaFuncSetAttribute(roi_pool_fwd_persist_kernel<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FRCNN_CUDA(cudaFuncSetAttribute(roi_pool_fwd_persist_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FRCNN_CUDA(cudaFuncSetAttribute(roi_pool_fwd_persist_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    static int sm_count[64] = {};
+    int sms = (dev >= 0 && dev < 64) ? sm_count[dev] : 0;
+    if (!sms) {
+        FRCNN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if (dev >= 0 && dev < 64) sm_count[dev] = sms;
+    }
+    const TensorMaps* maps = nullptr;
+    const int rc = get_tensor_maps(feat, (long long)B * Hf * Wf, C, dev, &maps);
+    if (rc) return rc;
+    unsigned* counter = static_cast<unsigned*>(workspace);
+    RoiRecord* recs = reinterpret_cast<RoiRecord*>(static_cast<unsigned char*>(workspace) + 256);
+    const int n_rois = B * R, n_items = n_rois * (C / kWarpCh);
+    const int ctas = min((n_items + kWarps - 1) / kWarps, (512 / kThreads) * sms);
+    roi_records_kernel<<<(n_rois + 3) / 4, 128, 0, st>>>((const float4*)rois, n_rois, R, Hf, Wf, recs, counter,
+                                                        2u * (unsigned)(ctas * kWarps));
+    FRCNN_LAUNCH_CHECK("roi_records_kernel");
+    if (codes) {
+        if (C == 1024) roi_pool_fwd_persist_kernel<1024, true><<<ctas, kThreads, smem, st>>>(*maps, feat, Hf, Wf, C, recs, n_items, out, codes, counter);
+        else roi_pool_fwd_persist_kernel<0, true><<<ctas, kThreads, smem, st>>>(*maps, feat, Hf, Wf, C, recs, n_items, out, codes, counter);
+    } else {
+        if (C == 1024) roi_pool_fwd_persist_kernel<1024, false><<<ctas, kThreads, smem, st>>>(*maps, feat, Hf, Wf, C, recs, n_items, out, nullptr, counter);
+        else roi_pool_fwd_persist_kernel<0, false><<<ctas, kThreads, smem, st>>>(*maps, feat, Hf, Wf, C, recs, n_items, out, nullptr, counter);
+    }
+    FRCNN_LAUNCH_CHECK("roi_pool_fwd_persist_kernel");
     return 0;
 }
 

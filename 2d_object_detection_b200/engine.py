@@ -14,7 +14,7 @@ class ProposalRoIEngine:
     another.  The proposal buffers are double-buffered and guarded by events, so results are identical to the
     serial order.  ``overlap=False`` issues everything on the current stream (latency measurement)."""
 
-    KERNELS_PER_STEP = 4  # decode_filter, nms_select, finalize, roi_pool_fwd
+    KERNELS_PER_STEP = 5  # decode_filter, nms_select, finalize, roi_records, roi_pool_fwd
 
     def __init__(self, image_shape, batch, grid_shape, channels, num_anchors, score_threshold, iou_threshold,
                  max_total_size, pooled_size=7, kernel_size=2, pre_nms_top_n=None, overlap=True):
@@ -34,6 +34,8 @@ class ProposalRoIEngine:
         self._classes = mk(self.B, self.R, dtype=torch.int32)
         self._num_valid = mk(self.B, dtype=torch.int32)
         self.pooled = torch.empty((self.B, self.R, self.P, self.P, self.C), dtype=torch.float32, device=dev)
+        self.pool_ws_bytes = self._lib.frcnn_roi_pool_workspace_bytes(self.B, self.R, self.C, self.P, self.k)
+        self.pool_ws = torch.empty(max(self.pool_ws_bytes, 16), dtype=torch.uint8, device=dev)  # pools run one at a time (one stream)
         self._i = 0
         self.s_prop = torch.cuda.Stream(device=dev, priority=-1)  # few large CTAs: let them in ahead of the pool grid
         self.s_pool = torch.cuda.Stream(device=dev)
@@ -74,7 +76,14 @@ class ProposalRoIEngine:
 
     def _pool(self, j, feature_maps):
         check(self._lib.frcnn_roi_pool_forward(ptr(feature_maps), self.B, self.Hf, self.Wf, self.C, ptr(self._rois[j]),
-                                               self.R, self.P, self.k, ptr(self.pooled), stream()), "roi_pool_forward")
+                                               self.R, self.P, self.k, ptr(self.pooled), ptr(self.pool_ws), self.pool_ws_bytes,
+                                               stream()), "roi_pool_forward")
+
+    def reset_pipeline(self):
+        """Forget the events of earlier steps (call after ``drain()`` + a synchronisation, e.g. before capturing a block of
+        steps in a CUDA graph: a captured stream must not wait on an event recorded outside the capture)."""
+        self._i = 0
+        self._pool_recorded = [False, False]
 
     def attach(self):
         """Make both pipeline streams wait for work already queued on the caller's current stream."""
@@ -140,7 +149,7 @@ class TrainStepEngine:
     features and the RCNN predictions are the caller's: ``rcnn_scores`` / ``rcnn_boxes`` / ``d_pooled`` are its tensors
     (bench.py passes synthetic ones)."""
 
-    KERNELS_PER_STEP = 17  # 2 gathers, 3 postprocess, 2+1 RPN targets/samples, 1 loss, 1 pool fwd, 1 scale, 2+1 RCNN, 1 loss, 1 pool bwd (+ 3 memsets)
+    KERNELS_PER_STEP = 18  # 2 gathers, 3 postprocess, 2+1 RPN targets/samples, 1 loss, 2 pool fwd (records + pool), 1 scale, 2+1 RCNN, 1 loss, 1 pool bwd (+ 3 memsets)
 
     def __init__(self, image_shape, batch, grid_shape, channels, anchors, num_classes, rpn_config, rcnn_config,
                  max_num_objects=100, pre_nms_top_n=None):
@@ -185,6 +194,7 @@ class TrainStepEngine:
         self.ws_tgt_rcnn = ws(L_.frcnn_generate_targets_workspace_bytes(B, R))
         self.ws_smp_rpn = ws(L_.frcnn_sample_indices_workspace_bytes(B, Nv))
         self.ws_smp_rcnn = ws(L_.frcnn_sample_indices_workspace_bytes(B, R))
+        self.ws_pool = ws(L_.frcnn_roi_pool_workspace_bytes(B, R, C, self.P, self.k))
         self._step = 0
 
     def algorithmic_bytes(self):
@@ -232,7 +242,8 @@ class TrainStepEngine:
         self._samples(self.rpn_tl, self.rpn_tb, Nv, 2, sm, self.scores_v, self.deltas_v, self.rpn_samples, self.ws_smp_rpn,
                       2 * seed)
         check(L_.frcnn_roi_pool_forward_argmax(ptr(feature_maps), B, self.Hf, self.Wf, self.C, ptr(self.rois), R, self.P, self.k,
-                                               ptr(self.pooled), ptr(self.codes), stream()), "roi_pool_forward_argmax")
+                                               ptr(self.pooled), ptr(self.codes), ptr(self.ws_pool[0]), self.ws_pool[1], stream()),
+              "roi_pool_forward_argmax")
         if between is not None:
             between()  # e.g. the caller's Dense heads on self.pooled producing rcnn_scores / rcnn_boxes
         check(L_.frcnn_scale_boxes(ptr(self.rois), B * R, H, W, 0, ptr(self.rois_abs), stream()), "to_absolute")

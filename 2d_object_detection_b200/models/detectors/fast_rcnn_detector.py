@@ -5,7 +5,7 @@ from __future__ import annotations
 
 import torch
 
-from ..._tensor import as_device, check, lib, ptr, stream
+from ..._tensor import as_device, check, lib, ptr, stream, workspace
 from ...utils.boxes import to_absolute
 from ...utils.training import get_training_samples as _get_training_samples
 
@@ -20,7 +20,10 @@ def roi_pool_forward(feature_maps, rois, pooled_size, kernel_size):
     R = r.shape[1]
     P, k = int(pooled_size), int(kernel_size)
     out = torch.empty((B, R, P, P, C), dtype=torch.float32, device=f.device)
-    check(lib().frcnn_roi_pool_forward(ptr(f), B, Hf, Wf, C, ptr(r), R, P, k, ptr(out), stream()), "roi_pool_forward")
+    ws_bytes = lib().frcnn_roi_pool_workspace_bytes(B, R, C, P, k)
+    ws = workspace(ws_bytes)
+    check(lib().frcnn_roi_pool_forward(ptr(f), B, Hf, Wf, C, ptr(r), R, P, k, ptr(out), ptr(ws), ws_bytes, stream()),
+          "roi_pool_forward")
     return out
 
 
@@ -48,8 +51,10 @@ def roi_pool_forward_argmax(feature_maps, rois, pooled_size, kernel_size):
     P, k = int(pooled_size), int(kernel_size)
     out = torch.empty((B, R, P, P, C), dtype=torch.float32, device=f.device)
     codes = torch.empty((B, R, P, P, C // 4), dtype=torch.uint8, device=f.device)
-    check(lib().frcnn_roi_pool_forward_argmax(ptr(f), B, Hf, Wf, C, ptr(r), R, P, k, ptr(out), ptr(codes), stream()),
-          "roi_pool_forward_argmax")
+    ws_bytes = lib().frcnn_roi_pool_workspace_bytes(B, R, C, P, k)
+    ws = workspace(ws_bytes)
+    check(lib().frcnn_roi_pool_forward_argmax(ptr(f), B, Hf, Wf, C, ptr(r), R, P, k, ptr(out), ptr(codes), ptr(ws), ws_bytes,
+                                              stream()), "roi_pool_forward_argmax")
     return out, codes
 
 

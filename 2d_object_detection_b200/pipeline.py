@@ -34,13 +34,15 @@ class ProposalRoIPipeline:
         self.score_threshold, self.iou_threshold = float(score_threshold), float(iou_threshold)
         self.pre_nms_top_n = int(pre_nms_top_n or 0)
         self._h = C.c_void_p()
+        self._seq = 0
         check(lib().frcnn_pipeline_create(C.byref(self._h), self.B, self.Hf, self.Wf, self.C, self.N, self.R, self.P,
                                           self.k), "pipeline_create")
         mk = (lambda *s, dtype=torch.float32: torch.empty(s, dtype=dtype, pin_memory=pin))
-        self.rois = mk(self.B, self.R, 4)
-        self.roi_scores = mk(self.B, self.R)
-        self.num_valid = mk(self.B, dtype=torch.int32)
-        self.pooled = mk(self.B, self.R, self.P, self.P, self.C)
+        # two sets of host output buffers: batch i + 1 may be submitted while batch i is still landing
+        self._out = [(mk(self.B, self.R, 4), mk(self.B, self.R), mk(self.B, dtype=torch.int32),
+                      mk(self.B, self.R, self.P, self.P, self.C)) for _ in range(2)]
+        self._last = 0
+        self._tickets = {}
 
     @property
     def h2d_bytes(self):
@@ -50,16 +52,38 @@ class ProposalRoIPipeline:
     def d2h_bytes(self):
         return 4 * (self.B * self.R * 5 + self.B + self.B * self.R * self.P * self.P * self.C)
 
+    # results of the most recently completed batch
+    rois = property(lambda self: self._out[self._last][0])
+    roi_scores = property(lambda self: self._out[self._last][1])
+    num_valid = property(lambda self: self._out[self._last][2])
+    pooled = property(lambda self: self._out[self._last][3])
+
+    def submit(self, regions, pred_scores, pred_boxes, feature_maps, copy_pooled=True):
+        """Enqueue one batch (copies + kernels) and return a ticket at once; at most two batches in flight.  The input
+        arrays must stay untouched until ``wait(ticket)`` returns."""
+        t = C.c_int32(-1)
+        o = self._out[self._seq & 1]  # the library's device slot for this batch is ticket % 2 as well
+        check(lib().frcnn_pipeline_submit(self._h, float(self.image_shape[0]), float(self.image_shape[1]),
+                                          _host_ptr(regions), _host_ptr(pred_scores), _host_ptr(pred_boxes),
+                                          _host_ptr(feature_maps), self.score_threshold, self.iou_threshold,
+                                          self.pre_nms_top_n, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(),
+                                          o[3].data_ptr() if copy_pooled else None, C.byref(t)), "pipeline_submit")
+        self._tickets[t.value] = o
+        self._seq = t.value + 1
+        return t.value
+
+    def wait(self, ticket):
+        """Block until the batch behind ``ticket`` has landed; returns its host tensors
+        (rois [B,R,4], roi_scores [B,R], num_valid [B], pooled [B,R,P,P,C])."""
+        check(lib().frcnn_pipeline_wait(self._h, int(ticket)), "pipeline_wait")
+        o = self._tickets.pop(int(ticket))
+        self._last = int(ticket) & 1
+        return o
+
     def __call__(self, regions, pred_scores, pred_boxes, feature_maps, copy_pooled=True):
         """regions [N,4], pred_scores [B,N,2], pred_boxes [B,N,1,4], feature_maps [B,Hf,Wf,C]: host fp32.
         Returns host tensors (rois [B,R,4], roi_scores [B,R], num_valid [B], pooled [B,R,P,P,C])."""
-        check(lib().frcnn_pipeline_run(self._h, float(self.image_shape[0]), float(self.image_shape[1]),
-                                       _host_ptr(regions), _host_ptr(pred_scores), _host_ptr(pred_boxes),
-                                       _host_ptr(feature_maps), self.score_threshold, self.iou_threshold,
-                                       self.pre_nms_top_n, self.rois.data_ptr(), self.roi_scores.data_ptr(),
-                                       self.num_valid.data_ptr(), self.pooled.data_ptr() if copy_pooled else None),
-              "pipeline_run")
-        return self.rois, self.roi_scores, self.num_valid, self.pooled
+        return self.wait(self.submit(regions, pred_scores, pred_boxes, feature_maps, copy_pooled))
 
     def close(self):
         if self._h:

@@ -85,6 +85,8 @@ WORKLOADS = {
     # configs[3]: dense-anchor stress 800x1333, 50x84 grid, 28 anchors/location, pre 12000 / post 1000.
     "dense_b16": Workload("dense_b16", (800, 1333, 3), (0.125, 0.177, 0.25, 0.354, 0.5, 0.707, 1.0),
                           (0.5, 1.0, 2.0, 3.0), 16, 12000, 1000),
+    # configs[4]: training path, KITTI shape, batch 16 per GPU, training-mode RPN (anchors inside the image, no pre-NMS cap).
+    "train_b16": Workload("train_b16", (375, 1242, 3), (0.25, 0.5, 1.0), _R3, 16, None, 300),
     # config.json default of the reference (600x1987, 12 anchors, no cap).
     "default_b2": Workload("default_b2", (600, 1987, 3), (0.25, 0.5, 1.0, 2.0), _R3, 2, None, 300),
 }

@@ -152,8 +152,13 @@ FRCNN_API int frcnn_nms(const float* boxes, const float* scores, int segments, i
  * ceil(in) == floor(in) for the right / bottom neighbour; the walk and streaming kernels read the pixel after it with
  * weight exactly 0 -- (next - a) * 0 == 0 for finite data, NaN if that extra pixel is Inf / NaN
  * (tests: test_roi_pool_integer_positions_read_one_pixel_further_finite_inputs). */
+/* Scratch for the row-streaming kernels: a work counter and one 512-byte record per RoI (built by a pre-kernel on the same
+ * stream: sample offsets / weights, the feature rows of the walk, ring geometry).  0 for shapes that do not use them.
+ * Launches that may overlap (different streams) need different workspaces. */
+FRCNN_API size_t frcnn_roi_pool_workspace_bytes(int B, int R, int C, int pooled_size, int kernel_size);
 FRCNN_API int frcnn_roi_pool_forward(const float* feature_maps, int B, int Hf, int Wf, int C, const float* rois, int R,
-                           int pooled_size, int kernel_size, float* out, frcnn_stream_t stream);
+                           int pooled_size, int kernel_size, float* out, void* workspace, size_t workspace_bytes,
+                           frcnn_stream_t stream);
 
 /* Gradient w.r.t. feature_maps (models/faster_rcnn.py:73,103 through :168 and :160): MaxPoolGrad to
  * the first maximum in row-major window order, then CropAndResizeGradImage.  dfeature [B,Hf,Wf,C] is
@@ -171,7 +176,7 @@ FRCNN_API int frcnn_roi_pool_backward(const float* feature_maps, int B, int Hf, 
 FRCNN_API int frcnn_roi_pool_argmax_supported(int C, int pooled_size, int kernel_size);
 FRCNN_API int frcnn_roi_pool_forward_argmax(const float* feature_maps, int B, int Hf, int Wf, int C, const float* rois, int R,
                                   int pooled_size, int kernel_size, float* out, unsigned char* argmax_codes,
-                                  frcnn_stream_t stream);
+                                  void* workspace, size_t workspace_bytes, frcnn_stream_t stream);
 FRCNN_API int frcnn_roi_pool_backward_argmax(int B, int Hf, int Wf, int C, const float* rois, int R, int pooled_size,
                                    int kernel_size, const float* dy, const unsigned char* argmax_codes, float* dfeature,
                                    frcnn_stream_t stream);
@@ -257,6 +262,16 @@ FRCNN_API int frcnn_pipeline_run(frcnn_pipeline_t* p, float image_height, float 
                        const float* pred_scores, const float* pred_boxes, const float* feature_maps,
                        float score_threshold, float iou_threshold, int pre_nms_top_n, float* rois, float* roi_scores,
                        int32_t* num_valid, float* pooled);
+/* The same, split: submit enqueues the copies and kernels of one batch and returns a ticket without waiting; wait blocks
+ * until that batch's outputs have landed in the host buffers.  The device buffers exist twice, so batch i + 1 may be
+ * submitted before batch i is waited for (at most two batches in flight; a third submit waits for the oldest): the
+ * upstream copies of the next batch then overlap the downstream copies of the current one (PCIe is full duplex).  Input
+ * and output host buffers must stay untouched between a submit and its wait.  run == submit + wait. */
+FRCNN_API int frcnn_pipeline_submit(frcnn_pipeline_t* p, float image_height, float image_width, const float* regions,
+                          const float* pred_scores, const float* pred_boxes, const float* feature_maps,
+                          float score_threshold, float iou_threshold, int pre_nms_top_n, float* rois, float* roi_scores,
+                          int32_t* num_valid, float* pooled, int32_t* ticket);
+FRCNN_API int frcnn_pipeline_wait(frcnn_pipeline_t* p, int32_t ticket);
 
 #ifdef __cplusplus
 }

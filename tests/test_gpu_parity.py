@@ -842,7 +842,8 @@ def test_train_step_engine_matches_composed_calls_and_is_graph_capturable(det, o
     for k in ("target_labels", "pred_scores", "target_boxes", "pred_boxes"):
         assert torch.equal(smp7[k], eng.rcnn_samples[k]), k
     g_ref = det.roi_pool_backward_argmax(tuple(args[2].shape), eng.rois, args[7], codes, 7, 2)
-    assert torch.equal(g_ref, eng.d_feature)
+    # (TMA reduce-adds of different RoIs reach a pixel in a different order on every launch: equal to rounding only)
+    assert float((g_ref - eng.d_feature).abs().max()) <= 2e-5 * float(g_ref.abs().max())
     ref_g = orc.roi_pool_backward(f, host(eng.rois), dy, 7, 2)
     np.testing.assert_allclose(host(eng.d_feature), ref_g, rtol=RTOL, atol=RTOL * np.abs(ref_g).max())
     eager = {k: v.clone() for k, v in (("rois", eng.rois), ("pooled", eng.pooled), ("codes", eng.codes), ("dfeat", eng.d_feature),
