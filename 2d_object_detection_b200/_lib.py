@@ -44,6 +44,7 @@ SIGNATURES = {
     "frcnn_nms_workspace_bytes": (_sz, [_i, _i]),
     "frcnn_nms": (_i, [_p, _p, _i, _i, _f, _f, _i, _i, _p, _p, _p, _p, _sz, _p]),
     "frcnn_roi_pool_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "frcnn_roi_pool_set_max_sms": (_i, [_i]),
     "frcnn_roi_pool_forward": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _i, _p, _p, _sz, _p]),
     "frcnn_roi_pool_backward": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _i, _p, _p, _p]),
     "frcnn_roi_pool_argmax_supported": (_i, [_i, _i, _i]),

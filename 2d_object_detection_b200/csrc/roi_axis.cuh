@@ -39,6 +39,7 @@ int launch_roi_pool_fwd_stream(const float* feat, int B, int Hf, int Wf, int C, 
                                unsigned char* codes, cudaStream_t st);
 // Persistent form (the one the library uses): per-RoI records + warp-persistent pooling kernel; workspace = counter + records.
 size_t roi_pool_stream_workspace_bytes(int B, int R);
+void roi_pool_set_max_sms(int max_sms);
 int launch_roi_pool_fwd_persist(const float* feat, int B, int Hf, int Wf, int C, const float* rois, int R, float* out,
                                 unsigned char* codes, void* workspace, size_t workspace_bytes, cudaStream_t st);
 

@@ -774,6 +774,11 @@ using namespace frcnn;
 
 extern "C" {
 
+int frcnn_roi_pool_set_max_sms(int max_sms) {
+    roi_pool_set_max_sms(max_sms);
+    return 0;
+}
+
 size_t frcnn_roi_pool_workspace_bytes(int B, int R, int C, int P, int k) {
     if (B <= 0 || R <= 0 || !roi_pool_stream_supported(C, P, k) || kForceBinRowWalk) return 0;
     return roi_pool_stream_workspace_bytes(B, R);

@@ -8,7 +8,7 @@
 //   * roi_records_kernel (one warp per RoI, a few microseconds per launch) turns every RoI into a 512-byte RECORD once:
 //     sample offsets / weights, the walk's row list and bit string, box class, ring geometry (fast_rcnn_detector.py:157-168
 //     reads the same boxes once per crop_and_resize call).
-//   * roi_pool_fwd_persist_kernel runs 4 independent WARPS per CTA, 4 CTAs per SM, and every warp is its own worker: it
+//   * roi_pool_fwd_persist_kernel runs 16 independent WARPS per CTA, one CTA per SM, and every warp is its own worker: it
 //     pulls (RoI, 64-channel) items from a global counter -- the first two are static, then one atomicAdd per item, issued
 //     two items ahead -- copies the item's record into shared memory with one cp.async.bulk (triple-buffered), and never
 //     synchronises with another warp.
@@ -30,7 +30,12 @@ constexpr int kRecBufs = 3;
 constexpr int kPBarBytes = 128;           // 8 row + 3 record barriers, padded
 constexpr int kPWarpBytes = kWarpRingBytes + kRecBufs * kRecBytes + kPBarBytes;  // 14208 B per warp, 56832 B per CTA
 static_assert(kPWarpBytes % 128 == 0, "per-warp shared-memory region must keep the rings 128-byte aligned");
-static_assert(4 * (kWarps * kPWarpBytes + 1024) <= 228 * 1024, "4 CTAs per SM must fit");
+// ONE 16-warp CTA per SM (its warps never synchronise, so the CTA size is free): a grid of n CTAs occupies exactly n SMs and
+// leaves the others completely empty -- the caller can keep a few SMs for kernels of other streams (the proposal path of
+// the next batch needs whole SMs: 1024-thread NMS CTAs), see frcnn_roi_pool_set_max_sms.
+constexpr int kPWarps = 16;
+constexpr int kPThreads = kPWarps * 32;
+static_assert(kPWarps * kPWarpBytes <= 227 * 1024, "one CTA per SM must fit");
 
 enum : unsigned char { kClsSmall = 0, kClsLarge = 1, kClsGather = 2 };
 
@@ -187,7 +192,7 @@ __device__ __forceinline__ PItem load_item(unsigned rec, int half) {
 
 // kC = number of channels when known at compile time (1024), 0 = any; kCodes: also write the arg-max codes.
 template <int kC, bool kCodes>
-__global__ void __launch_bounds__(kThreads, 512 / kThreads)
+__global__ void __launch_bounds__(kPThreads, 1)
     roi_pool_fwd_persist_kernel(const __grid_constant__ TensorMaps maps, const float* __restrict__ feat, int Hf, int Wf, int C_,
                                 const RoiRecord* __restrict__ recs, int n_items, float* __restrict__ out,
                                 unsigned char* __restrict__ codes, unsigned* __restrict__ counter) {
@@ -204,8 +209,8 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    const int total_warps = gridDim.x * kWarps;
-    int idx_cur = blockIdx.x * kWarps + warp;  // the first two items are static; the counter starts at 2 * total_warps
+    const int total_warps = gridDim.x * kPWarps;
+    int idx_cur = blockIdx.x * kPWarps + warp;  // the first two items are static; the counter starts at 2 * total_warps
     int idx_nxt = idx_cur + total_warps;
     if (idx_cur >= n_items) return;
     const float onef = kOne;
@@ -329,9 +334,7 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads)
             u64 prog = ((u64)uniform(lds_u32(it.rec + 176)) << 32) | uniform(lds_u32(it.rec + 172));
             const unsigned nba = uniform(lds_u32(it.rec + 188));
             const int n_before = (int)((nba >> 8) & 0xffu), n_after = (int)((nba >> 16) & 0xffu);
-            u64 X0[kS], X1[kS];
-#pragma unroll
-            for (int i = 0; i < kS; ++i) X0[i] = X1[i] = 0ull;
+            u64 X0[kS], X1[kS];  // (always written by load_row before a crop row inside the map reads them)
             float2 M[kP];
             int sy = 0;
             float yl_next = lds_f32(it.rec + 112);  // the y weight of the next crop row, loaded one crop row ahead
@@ -343,18 +346,21 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads)
                 const unsigned bit = it.bar + slot;
                 mbar_wait(bar_s + bit * 8, (row_phase >> bit) & 1u);
                 row_phase ^= 1u << bit;
-                float wx[16];
 #pragma unroll
-                for (int q = 0; q < 4; ++q)  // record bytes 0 .. 63: wx[0..13] (+ the first two sample offsets, unused)
-                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                                 : "=f"(wx[4 * q]), "=f"(wx[4 * q + 1]), "=f"(wx[4 * q + 2]), "=f"(wx[4 * q + 3])
-                                 : "r"(it.rec + 16 * q));
+                for (int h = 0; h < 2; ++h) {  // samples 0..7, then 8..13: the x weights come eight at a time (two broadcast
+                    float wx[8];               // 128-bit loads of record bytes 0..63), which keeps fewer of them alive
 #pragma unroll
-                for (int i = 0; i < kS; ++i) {
-                    u64 l, r;
-                    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(l) : "r"(aoff[i] + slot_off));
-                    asm volatile("ld.shared.b64 %0, [%1+256];" : "=l"(r) : "r"(aoff[i] + slot_off));
-                    X[i] = lerp2(l, r, pack2(wx[i], wx[i]), one);
+                    for (int q = 0; q < 2; ++q)
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                     : "=f"(wx[4 * q]), "=f"(wx[4 * q + 1]), "=f"(wx[4 * q + 2]), "=f"(wx[4 * q + 3])
+                                     : "r"(it.rec + 32 * h + 16 * q));
+#pragma unroll
+                    for (int i = 8 * h; i < (h ? kS : 8); ++i) {
+                        u64 l, r;
+                        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(l) : "r"(aoff[i] + slot_off));
+                        asm volatile("ld.shared.b64 %0, [%1+256];" : "=l"(r) : "r"(aoff[i] + slot_off));
+                        X[i] = lerp2(l, r, pack2(wx[i - 8 * h], wx[i - 8 * h]), one);
+                    }
                 }
                 __syncwarp();  // every lane has consumed its operands: the slot may be overwritten
                 if (k + it.depth < it.n_rows) stage(it, ch0, k + it.depth, slot);
@@ -368,7 +374,7 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads)
             // One finished crop row: fold it into the bin maxima; after the second row of a bin-row store the 7 bins.
             auto emit = [&](const u64(&T)[kS], const u64(&Bm)[kS], bool outside) {
                 const float yl = yl_next;
-                yl_next = lds_f32(it.rec + 112 + 4 * min(sy + 1, kS - 1));
+                yl_next = lds_f32(it.rec + 112 + 4 * (sy + 1));  // (after the last crop row this reads the word behind ylerp: unused)
                 if (!(sy & 1)) {
                     ca = cb = 0u;
                     if (outside) {  // crop row outside the map: extrapolation value 0 takes part in the max
@@ -408,21 +414,23 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads)
                 ++sy;
             };
             for (int i = 0; i < n_before; ++i) emit(X0, X1, true);
+            if (it.n_rows > 0) {
 #pragma unroll 1
-            for (int kk = 0; kk < it.n_rows; kk += 2) {
-                load_row(X0);  // even position: the new bottom row lands in set 0, set 1 holds the top row
-                prog >>= 1;
-                while (prog & 1ull) {
-                    emit(X1, X0, false);
+                for (;;) {  // (the exit in the middle keeps the second half unconditional: no merge copies of a row set)
+                    load_row(X0);  // even position: the new bottom row lands in set 0, set 1 holds the top row
                     prog >>= 1;
-                }
-                if (kk + 1 < it.n_rows) {
+                    while (prog & 1ull) {
+                        emit(X1, X0, false);
+                        prog >>= 1;
+                    }
+                    if (k >= it.n_rows) break;
                     load_row(X1);
                     prog >>= 1;
                     while (prog & 1ull) {
                         emit(X0, X1, false);
                         prog >>= 1;
                     }
+                    if (k >= it.n_rows) break;
                 }
             }
             for (int i = 0; i < n_after; ++i) emit(X0, X1, true);

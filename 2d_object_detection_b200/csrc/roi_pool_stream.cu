@@ -24,6 +24,8 @@
 #include <cudaTypedefs.h>
 #include <stddef.h>
 
+#include <atomic>
+
 #include "roi_axis.cuh"
 
 namespace frcnn {
@@ -1099,6 +1101,9 @@ int launch_roi_pool_fwd_stream(const float* feat, int B, int Hf, int Wf, int C, 
     return 0;
 }
 
+static std::atomic<int> g_roi_pool_max_sms{0};
+void roi_pool_set_max_sms(int max_sms) { g_roi_pool_max_sms.store(max_sms > 0 ? max_sms : 0, std::memory_order_relaxed); }
+
 size_t roi_pool_stream_workspace_bytes(int B, int R) { return 256 + (size_t)kRecStride * (size_t)B * (size_t)R; }
 
 // Persistent forward: records pre-kernel + warp-persistent pooling kernel.  workspace: [counter | records].
@@ -1109,7 +1114,7 @@ int launch_roi_pool_fwd_persist(const float* feat, int B, int Hf, int Wf, int C,
     FRCNN_REQUIRE(Hf <= 65535 && Wf <= 65535, FRCNN_ELIMIT, "roi_pool_forward: feature map side beyond 65535");
     FRCNN_REQUIRE((int64_t)B * Hf * Wf < (1ll << 31) && (int64_t)B * R * (C / kWarpCh) < (1ll << 30), FRCNN_ELIMIT,
                   "roi_pool_forward: tensor too large");
-    const size_t smem = (size_t)kWarps * kPWarpBytes;
+    const size_t smem = (size_t)kPWarps * kPWarpBytes;
     int dev = 0;
     FRCNN_CUDA(cudaGetDevice(&dev));
     static bool configured[64] = {};
@@ -1132,16 +1137,17 @@ int launch_roi_pool_fwd_persist(const float* feat, int B, int Hf, int Wf, int C,
     unsigned* counter = static_cast<unsigned*>(workspace);
     RoiRecord* recs = reinterpret_cast<RoiRecord*>(static_cast<unsigned char*>(workspace) + 256);
     const int n_rois = B * R, n_items = n_rois * (C / kWarpCh);
-    const int ctas = min((n_items + kWarps - 1) / kWarps, (512 / kThreads) * sms);
+    const int budget = g_roi_pool_max_sms.load(std::memory_order_relaxed);
+    const int ctas = min((n_items + kPWarps - 1) / kPWarps, budget > 0 ? min(budget, sms) : sms);  // one CTA per SM
     roi_records_kernel<<<(n_rois + 3) / 4, 128, 0, st>>>((const float4*)rois, n_rois, R, Hf, Wf, recs, counter,
-                                                        2u * (unsigned)(ctas * kWarps));
+                                                        2u * (unsigned)(ctas * kPWarps));
     FRCNN_LAUNCH_CHECK("roi_records_kernel");
     if (codes) {
-        if (C == 1024) roi_pool_fwd_persist_kernel<1024, true><<<ctas, kThreads, smem, st>>>(*maps, feat, Hf, Wf, C, recs, n_items, out, codes, counter);
-        else roi_pool_fwd_persist_kernel<0, true><<<ctas, kThreads, smem, st>>>(*maps, feat, Hf, Wf, C, recs, n_items, out, codes, counter);
+        if (C == 1024) roi_pool_fwd_persist_kernel<1024, true><<<ctas, kPThreads, smem, st>>>(*maps, feat, Hf, Wf, C, recs, n_items, out, codes, counter);
+        else roi_pool_fwd_persist_kernel<0, true><<<ctas, kPThreads, smem, st>>>(*maps, feat, Hf, Wf, C, recs, n_items, out, codes, counter);
     } else {
-        if (C == 1024) roi_pool_fwd_persist_kernel<1024, false><<<ctas, kThreads, smem, st>>>(*maps, feat, Hf, Wf, C, recs, n_items, out, nullptr, counter);
-        else roi_pool_fwd_persist_kernel<0, false><<<ctas, kThreads, smem, st>>>(*maps, feat, Hf, Wf, C, recs, n_items, out, nullptr, counter);
+        if (C == 1024) roi_pool_fwd_persist_kernel<1024, false><<<ctas, kPThreads, smem, st>>>(*maps, feat, Hf, Wf, C, recs, n_items, out, nullptr, counter);
+        else roi_pool_fwd_persist_kernel<0, false><<<ctas, kPThreads, smem, st>>>(*maps, feat, Hf, Wf, C, recs, n_items, out, nullptr, counter);
     }
     FRCNN_LAUNCH_CHECK("roi_pool_fwd_persist_kernel");
     return 0;

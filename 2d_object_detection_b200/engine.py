@@ -17,7 +17,7 @@ class ProposalRoIEngine:
     KERNELS_PER_STEP = 5  # decode_filter, nms_select, finalize, roi_records, roi_pool_fwd
 
     def __init__(self, image_shape, batch, grid_shape, channels, num_anchors, score_threshold, iou_threshold,
-                 max_total_size, pooled_size=7, kernel_size=2, pre_nms_top_n=None, overlap=True):
+                 max_total_size, pooled_size=7, kernel_size=2, pre_nms_top_n=None, overlap=True, reserve_sms=None):
         dev = require_cuda()
         self.image_shape = tuple(image_shape)
         self.B, (self.Hf, self.Wf), self.C, self.N = int(batch), grid_shape, int(channels), int(num_anchors)
@@ -26,6 +26,12 @@ class ProposalRoIEngine:
         self.pre_nms_top_n = int(pre_nms_top_n or 0)
         self.overlap = bool(overlap)
         self._lib = lib()
+        # The persistent RoI kernel takes one CTA per SM; the proposal path of the next step (one 1024-thread NMS CTA per
+        # image) needs whole SMs to run beside it, so the pipelined engine keeps `reserve_sms` SMs out of the pool's grid.
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        if reserve_sms is None:
+            reserve_sms = min(self.B, sms // 8) if self.overlap else 0
+        self.pool_sms = max(1, sms - int(reserve_sms)) if reserve_sms else 0  # 0 = every SM
         self.ws_bytes = self._lib.frcnn_postprocess_workspace_bytes(self.B, self.N, 1, self.R, self.R)
         self.ws = torch.empty(max(self.ws_bytes, 16), dtype=torch.uint8, device=dev)
         mk = lambda *s, dtype=torch.float32: [torch.empty(s, dtype=dtype, device=dev) for _ in range(2)]  # noqa: E731
@@ -75,6 +81,7 @@ class ProposalRoIEngine:
                                           None, None, ptr(self.ws), self.ws_bytes, stream()), "postprocess_output")
 
     def _pool(self, j, feature_maps):
+        self._lib.frcnn_roi_pool_set_max_sms(self.pool_sms)
         check(self._lib.frcnn_roi_pool_forward(ptr(feature_maps), self.B, self.Hf, self.Wf, self.C, ptr(self._rois[j]),
                                                self.R, self.P, self.k, ptr(self.pooled), ptr(self.pool_ws), self.pool_ws_bytes,
                                                stream()), "roi_pool_forward")

@@ -336,7 +336,7 @@ def bind_to_gpu_numa_node(local_rank):
         return {"node": None, "bound": False, "error": repr(e)[:80]}
 
 
-def measure_inference(ctx, w, syn, steps, warmup, min_seconds, with_e2e, e2e_seconds):
+def measure_inference(ctx, w, syn, steps, warmup, min_seconds, with_e2e, e2e_seconds, reserve_sms=None):
     torch, det = ctx.torch, ctx.det
     device, rank = ctx.device, ctx.rank
     B = w.batch
@@ -344,7 +344,7 @@ def measure_inference(ctx, w, syn, steps, warmup, min_seconds, with_e2e, e2e_sec
                                  [0, 0, w.image_shape[1], w.image_shape[0]])
     mk_engine = lambda overlap: det.engine.ProposalRoIEngine(  # noqa: E731
         w.image_shape, B, w.grid, w.channels, w.num_anchors, w.score_threshold, w.iou_threshold, w.max_total_size,
-        w.pooled_size, w.kernel_size, w.pre_nms_top_n, overlap=overlap)
+        w.pooled_size, w.kernel_size, w.pre_nms_top_n, overlap=overlap, reserve_sms=reserve_sms)
     eng = mk_engine(True)
     # Inputs larger than L2: rotate over n_sets input sets (each rank its own seeds = its own images)
     n_sets, set_bytes = input_sets(w)
@@ -419,10 +419,10 @@ def measure_inference(ctx, w, syn, steps, warmup, min_seconds, with_e2e, e2e_sec
     pool_ms = float(np.mean([a.elapsed_time(b) for a, b in pool_events[min(3, n_ev - 1):]]))
     alg = eng.algorithmic_bytes()
     achieved = alg["roi_pool_fwd"] / (pool_ms * 1e-3) / 1e9
-    kernel = "roi_pool_fwd_stream_kernel<1024>" if w.channels == 1024 else "roi_pool_fwd_stream_kernel"
+    kernel = "roi_pool_fwd_persist_kernel<1024>" if w.channels == 1024 else "roi_pool_fwd_persist_kernel"
     res = {
         "value": value, "ms_per_step": ms_per_step, "timed_region_s": ms_total * 1e-3, "block_reps": reps,
-        "step_latency_ms": step_latency_ms, "clocks": clocks,
+        "step_latency_ms": step_latency_ms, "clocks": clocks, "pool_sms": eng.pool_sms,
         "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": ctx.peak_gbs, "unit": "GB/s",
                      "frac": achieved / ctx.peak_gbs, "traffic": load_traffic(w.name, "roi_pool_fwd"),
                      "peak_source": ctx.peak_src, "algorithmic_bytes_per_launch": alg["roi_pool_fwd"], "kernel_ms": pool_ms,
@@ -600,7 +600,8 @@ def run_b200_arm(args, syn):
     if train:
         res = measure_train(ctx, w, syn, args.steps, args.warmup, args.min_seconds)
     else:
-        res = measure_inference(ctx, w, syn, args.steps, args.warmup, args.min_seconds, not args.no_e2e, args.e2e_seconds)
+        res = measure_inference(ctx, w, syn, args.steps, args.warmup, args.min_seconds, not args.no_e2e, args.e2e_seconds,
+                                args.reserve_sms)
     others = []
     if not args.no_others:
         for name in ("kitti_b1", "kitti_b8", "dense_b16", "train_b16"):
@@ -642,7 +643,7 @@ def run_b200_arm(args, syn):
         "gpu_launches": res["gpu_launches"], "clocks": res["clocks"], "host_cores": os.cpu_count(),
         "other_workloads": others,
     }
-    for k in ("step_latency_ms", "block_reps", "stage_algorithmic_bytes_per_step", "allreduce", "N_valid", "steps_timed"):
+    for k in ("step_latency_ms", "block_reps", "pool_sms", "stage_algorithmic_bytes_per_step", "allreduce", "N_valid", "steps_timed"):
         if k in res:
             line[k] = res[k]
     print(json.dumps(line), flush=True)
@@ -662,6 +663,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-others", action="store_true")
+    ap.add_argument("--reserve-sms", type=int, default=None,
+                    help="SMs the pipelined engine keeps free of the persistent RoI kernel for the proposal path (default: per-GPU batch)")
     args = ap.parse_args()
     # the synthetic-input module is NumPy only; load it without importing the CUDA package on the reference arm
     import importlib.util

@@ -156,6 +156,10 @@ FRCNN_API int frcnn_nms(const float* boxes, const float* scores, int segments, i
  * stream: sample offsets / weights, the feature rows of the walk, ring geometry).  0 for shapes that do not use them.
  * Launches that may overlap (different streams) need different workspaces. */
 FRCNN_API size_t frcnn_roi_pool_workspace_bytes(int B, int R, int C, int pooled_size, int kernel_size);
+/* The row-streaming kernels are persistent: one 16-warp CTA per SM, on every SM of the device by default.  A caller that
+ * overlaps them with kernels of other streams (e.g. the proposal path of the next batch, whose 1024-thread NMS CTAs need
+ * whole SMs) caps the SMs they occupy here; max_sms <= 0 = all SMs.  Process-wide setting, read at launch. */
+FRCNN_API int frcnn_roi_pool_set_max_sms(int max_sms);
 FRCNN_API int frcnn_roi_pool_forward(const float* feature_maps, int B, int Hf, int Wf, int C, const float* rois, int R,
                            int pooled_size, int kernel_size, float* out, void* workspace, size_t workspace_bytes,
                            frcnn_stream_t stream);
