@@ -49,7 +49,7 @@ SIGNATURES = {
     "frcnn_roi_pool_backward": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _i, _p, _p, _p]),
     "frcnn_roi_pool_argmax_supported": (_i, [_i, _i, _i]),
     "frcnn_roi_pool_forward_argmax": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _i, _p, _p, _p, _sz, _p]),
-    "frcnn_roi_pool_backward_argmax": (_i, [_i, _i, _i, _i, _p, _i, _i, _i, _p, _p, _p, _p]),
+    "frcnn_roi_pool_backward_argmax": (_i, [_i, _i, _i, _i, _p, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
     "frcnn_generate_targets_workspace_bytes": (_sz, [_i, _i]),
     "frcnn_generate_targets": (_i, [_p, _p, _i, _i, _i, _p, _i, _i, _f, _f, _f, _f, _f, _f, _p, _p, _p, _p, _p, _sz,
                                     _p]),

@@ -47,4 +47,7 @@ int launch_roi_pool_fwd_persist(const float* feat, int B, int Hf, int Wf, int C,
 int launch_roi_pool_bwd_stream(int B, int Hf, int Wf, int C, const float* rois, int R, const float* dy,
                                const unsigned char* codes, float* dfeat, cudaStream_t st);
 
+int launch_roi_pool_bwd_persist(int B, int Hf, int Wf, int C, const float* rois, int R, const float* dy,
+                                const unsigned char* codes, float* dfeat, void* workspace, size_t workspace_bytes, cudaStream_t st);
+
 }  // namespace frcnn

@@ -25,6 +25,11 @@ constexpr bool kLegacyStreamForward = true;
 #else
 constexpr bool kLegacyStreamForward = false;
 #endif
+#ifdef FRCNN_AB_LEGACY_STREAM_BWD
+constexpr bool kLegacyStreamBackward = true;
+#else
+constexpr bool kLegacyStreamBackward = false;
+#endif
 
 // ---- tiny vector abstraction: float4 (C % 4 == 0) or float -------------------------------------
 __device__ __forceinline__ float4 vload(const float4* p) { return __ldg(p); }
@@ -875,7 +880,8 @@ int frcnn_roi_pool_forward_argmax(const float* feat, int B, int Hf, int Wf, int 
 }
 
 int frcnn_roi_pool_backward_argmax(int B, int Hf, int Wf, int C, const float* rois, int R, int P, int k, const float* dy,
-                                   const unsigned char* argmax_codes, float* dfeat, frcnn_stream_t stream) {
+                                   const unsigned char* argmax_codes, float* dfeat, void* workspace, size_t workspace_bytes,
+                                   frcnn_stream_t stream) {
     FRCNN_REQUIRE(B > 0 && Hf > 0 && Wf > 0 && C > 0 && R >= 0 && B <= 65535, FRCNN_EINVAL, "roi_pool_backward_argmax: bad shape");
     FRCNN_REQUIRE(frcnn_roi_pool_argmax_supported(C, P, k) && (int64_t)Hf * Wf * (C / 4) < (1ll << 31), FRCNN_ELIMIT,
                   "roi_pool_backward_argmax: needs C %% 4 == 0, kernel_size == 2, pooled_size <= 8");
@@ -884,7 +890,10 @@ int frcnn_roi_pool_backward_argmax(int B, int Hf, int Wf, int C, const float* ro
     FRCNN_CUDA(cudaMemsetAsync(dfeat, 0, sizeof(float) * (size_t)B * Hf * Wf * C, as_stream(stream)));
     if (R == 0) return 0;
     if (roi_pool_stream_supported(C, P, k) && !kForceBinRowWalk)
-        return launch_roi_pool_bwd_stream(B, Hf, Wf, C, rois, R, dy, argmax_codes, dfeat, as_stream(stream));
+        return kLegacyStreamBackward
+                   ? launch_roi_pool_bwd_stream(B, Hf, Wf, C, rois, R, dy, argmax_codes, dfeat, as_stream(stream))
+                   : launch_roi_pool_bwd_persist(B, Hf, Wf, C, rois, R, dy, argmax_codes, dfeat, workspace, workspace_bytes,
+                                                 as_stream(stream));
     return launch_codes<1>(nullptr, B, Hf, Wf, C, rois, R, P, nullptr, const_cast<unsigned char*>(argmax_codes), dy, dfeat,
                            as_stream(stream));
 }

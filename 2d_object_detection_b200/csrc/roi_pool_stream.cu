@@ -961,6 +961,8 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads)
 }
 
 
+#include "roi_pool_persist_bwd.cuh"
+
 // Host side: the eight tensor maps of a feature tensor, cached by (pointer, shape).
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1150,6 +1152,45 @@ int launch_roi_pool_fwd_persist(const float* feat, int B, int Hf, int Wf, int C,
         else roi_pool_fwd_persist_kernel<0, false><<<ctas, kPThreads, smem, st>>>(*maps, feat, Hf, Wf, C, recs, n_items, out, nullptr, counter);
     }
     FRCNN_LAUNCH_CHECK("roi_pool_fwd_persist_kernel");
+    return 0;
+}
+
+// Persistent backward: records pre-kernel + warp-persistent kernel.  dfeat must have been zeroed on the same stream.
+int launch_roi_pool_bwd_persist(int B, int Hf, int Wf, int C, const float* rois, int R, const float* dy,
+                                const unsigned char* codes, float* dfeat, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    FRCNN_REQUIRE(workspace && workspace_bytes >= roi_pool_stream_workspace_bytes(B, R) && aligned16(workspace), FRCNN_EWORKSPACE,
+                  "roi_pool_backward: workspace too small (frcnn_roi_pool_workspace_bytes)");
+    FRCNN_REQUIRE(Hf <= 65535 && Wf <= 65535, FRCNN_ELIMIT, "roi_pool_backward: feature map side beyond 65535");
+    FRCNN_REQUIRE((int64_t)B * Hf * Wf < (1ll << 31) && (int64_t)B * R * kP * kP < (1ll << 31) &&
+                      (int64_t)B * R * (C / kWarpCh) < (1ll << 30),
+                  FRCNN_ELIMIT, "roi_pool_backward: tensor too large");
+    const size_t smem = (size_t)kPWarps * kPBwdWarpBytes;
+    int dev = 0;
+    FRCNN_CUDA(cudaGetDevice(&dev));
+    static bool configured[64] = {};
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        FRCNN_CUDA(cudaFuncSetAttribute(roi_pool_bwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    static int sm_count[64] = {};
+    int sms = (dev >= 0 && dev < 64) ? sm_count[dev] : 0;
+    if (!sms) {
+        FRCNN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if (dev >= 0 && dev < 64) sm_count[dev] = sms;
+    }
+    const BwdMaps* maps = nullptr;
+    const int rc = get_bwd_maps(dfeat, (long long)B * Hf * Wf, dy, codes, (long long)B * R * kP * kP, C, dev, &maps);
+    if (rc) return rc;
+    unsigned* counter = static_cast<unsigned*>(workspace);
+    RoiRecord* recs = reinterpret_cast<RoiRecord*>(static_cast<unsigned char*>(workspace) + 256);
+    const int n_rois = B * R, n_items = n_rois * (C / kWarpCh);
+    const int budget = g_roi_pool_max_sms.load(std::memory_order_relaxed);
+    const int ctas = min((n_items + kPWarps - 1) / kPWarps, budget > 0 ? min(budget, sms) : sms);
+    roi_records_kernel<<<(n_rois + 3) / 4, 128, 0, st>>>((const float4*)rois, n_rois, R, Hf, Wf, recs, counter,
+                                                        2u * (unsigned)(ctas * kPWarps));
+    FRCNN_LAUNCH_CHECK("roi_records_kernel");
+    roi_pool_bwd_persist_kernel<<<ctas, kPThreads, smem, st>>>(*maps, Hf, Wf, C, recs, n_items, dy, codes, dfeat, counter);
+    FRCNN_LAUNCH_CHECK("roi_pool_bwd_persist_kernel");
     return 0;
 }
 

@@ -156,7 +156,7 @@ class TrainStepEngine:
     features and the RCNN predictions are the caller's: ``rcnn_scores`` / ``rcnn_boxes`` / ``d_pooled`` are its tensors
     (bench.py passes synthetic ones)."""
 
-    KERNELS_PER_STEP = 18  # 2 gathers, 3 postprocess, 2+1 RPN targets/samples, 1 loss, 2 pool fwd (records + pool), 1 scale, 2+1 RCNN, 1 loss, 1 pool bwd (+ 3 memsets)
+    KERNELS_PER_STEP = 19  # 2 gathers, 3 postprocess, 2+1 RPN targets/samples, 1 loss, 2 pool fwd (records + pool), 1 scale, 2+1 RCNN, 1 loss, 2 pool bwd (records + pool) (+ 3 memsets)
 
     def __init__(self, image_shape, batch, grid_shape, channels, anchors, num_classes, rpn_config, rcnn_config,
                  max_num_objects=100, pre_nms_top_n=None):
@@ -266,8 +266,8 @@ class TrainStepEngine:
     def backward(self, d_pooled):
         """dL/d(pooled) [B,R,P,P,C] -> dL/d(feature_maps) from the saved arg-max codes."""
         check(self._lib.frcnn_roi_pool_backward_argmax(self.B, self.Hf, self.Wf, self.C, ptr(self.rois), self.R, self.P, self.k,
-                                                       ptr(d_pooled), ptr(self.codes), ptr(self.d_feature), stream()),
-              "roi_pool_backward_argmax")
+                                                       ptr(d_pooled), ptr(self.codes), ptr(self.d_feature), ptr(self.ws_pool[0]),
+                                                       self.ws_pool[1], stream()), "roi_pool_backward_argmax")
         return self.d_feature
 
     def step(self, pred_scores, pred_boxes, feature_maps, gt_labels, gt_boxes, rcnn_scores, rcnn_boxes, d_pooled, seed=None,

@@ -67,8 +67,10 @@ def roi_pool_backward_argmax(feature_shape, rois, dy, argmax_codes, pooled_size,
     if g.numel() != B * R * P * P * C:
         raise ValueError(f"dy has {g.numel()} elements, expected {B * R * P * P * C}")
     df = torch.empty((B, Hf, Wf, C), dtype=torch.float32, device=g.device)
-    check(lib().frcnn_roi_pool_backward_argmax(B, Hf, Wf, C, ptr(r), R, P, k, ptr(g), ptr(argmax_codes), ptr(df), stream()),
-          "roi_pool_backward_argmax")
+    ws_bytes = lib().frcnn_roi_pool_workspace_bytes(B, R, C, P, k)
+    ws = workspace(ws_bytes)
+    check(lib().frcnn_roi_pool_backward_argmax(B, Hf, Wf, C, ptr(r), R, P, k, ptr(g), ptr(argmax_codes), ptr(df), ptr(ws), ws_bytes,
+                                               stream()), "roi_pool_backward_argmax")
     return df
 
 

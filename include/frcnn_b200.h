@@ -183,7 +183,7 @@ FRCNN_API int frcnn_roi_pool_forward_argmax(const float* feature_maps, int B, in
                                   void* workspace, size_t workspace_bytes, frcnn_stream_t stream);
 FRCNN_API int frcnn_roi_pool_backward_argmax(int B, int Hf, int Wf, int C, const float* rois, int R, int pooled_size,
                                    int kernel_size, const float* dy, const unsigned char* argmax_codes, float* dfeature,
-                                   frcnn_stream_t stream);
+                                   void* workspace, size_t workspace_bytes, frcnn_stream_t stream);
 
 /* ---- utils/training.py:7-77 generate_targets (+ :123-143), batched over images -------------
  *   gt_labels [B,G,nc+1] one-hot, zero rows = padding; gt_boxes [B,G,4] rel;
