@@ -10,12 +10,11 @@
 //     a 3-slot ring that runs across item boundaries: while the last three bin-rows of an item are consumed, the first
 //     three of the next item are already in flight.
 //   * the x-scatter of a finished feature row is 14 straight-line read-modify-writes of a lane-private row buffer (a
-//     sample outside the map adds into a scratch pixel), then one cp.reduce.async.bulk.tensor adds the row to dFeature.
+//     sample outside the map scatters with both weights 0), then one cp.reduce.async.bulk.tensor adds the row to dFeature.
 #pragma once
 
-constexpr int kPBwdRowPix = 26;                              // row-buffer ring of a warp, pixels
-constexpr int kPBwdScratchOff = kPBwdRowPix * kPixBytes;     // two scratch pixels behind the ring
-constexpr int kPBwdDyOff = kPBwdScratchOff + 2 * kPixBytes;
+constexpr int kPBwdRowPix = 28;                              // row-buffer ring of a warp, pixels
+constexpr int kPBwdDyOff = kPBwdRowPix * kPixBytes;
 constexpr int kPBwdSlotBytes = kBwdDyBytes + kBwdCodeBytes;  // 1792 B of dY + 128 B of codes
 constexpr int kPBwdRecOff = kPBwdDyOff + kBwdDySlots * kPBwdSlotBytes;
 constexpr int kPBwdRecBufs = 2;
@@ -159,13 +158,18 @@ __global__ void __launch_bounds__(kPThreads, 1)
                 release_bin_row(py);
             }
         } else {
-            // aoff[i]: this lane's shared address of sample i's left pixel in row buffer 0; a sample outside the map (record
-            // offset 0 while the record reserves a zero pixel) scatters into the scratch pixels behind the ring
+            // aoff[i]: this lane's shared address of sample i's left pixel in row buffer 0.  A sample outside the map (record
+            // offset 0 while the record reserves a zero pixel) may hold a gradient -- the extrapolation value can win a
+            // window -- that goes nowhere: it scatters to pixel 0 with weights okf - xl = 0 - 0 and xl = 0, while a sample
+            // inside the map gets okf - xl = 1 - xl, the same rounding as before.
             int aoff[kS];
+            float okf[kS];
 #pragma unroll
             for (int i = 0; i < kS; ++i) {
                 const int a = (int)lds_u32(rec + 56 + 4 * i);
-                aoff[i] = (int)lane_s + ((first_off != 0 && a == 0) ? kPBwdScratchOff : a - first_off);
+                const bool outside = first_off != 0 && a == 0;
+                aoff[i] = (int)lane_s + (outside ? 0 : a - first_off);
+                okf[i] = outside ? 0.0f : 1.0f;
             }
             u64 prog = ((u64)uniform(lds_u32(rec + 176)) << 32) | uniform(lds_u32(rec + 172));
             u64 G0[kS], G1[kS];
@@ -212,7 +216,7 @@ __global__ void __launch_bounds__(kPThreads, 1)
 #pragma unroll
                     for (int i = 8 * h; i < (h ? kS : 8); ++i) {
                         const float xl = wx[i - 8 * h];
-                        const float xr = fsub(1.0f, xl);
+                        const float xr = fsub(okf[i], xl);
                         const unsigned a = (unsigned)aoff[i] + rbuf_off;
                         const u64 lo = lds64(a), hi = lds64(a + kPixBytes);
                         sts64(a, fma2(G[i], pack2(xr, xr), lo));
