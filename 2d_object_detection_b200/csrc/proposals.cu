@@ -93,7 +93,8 @@ __global__ void score_keys_kernel(const float* __restrict__ scores, int64_t n, f
 // Stage 2: segmented greedy NMS.
 // ------------------------------------------------------------------------------------------------
 constexpr int kNmsThreads = 1024;
-constexpr int kChunk = 1024;         // candidates ordered + resolved per iteration (one per thread in the sort)
+constexpr int kChunk = 1024;         // candidates whose boxes are staged + resolved at a time (sub-chunk of the sorted list)
+constexpr int kList = 4096;          // candidates selected + sorted per refill (a refill = one radix select over all N keys)
 constexpr int kBins = 2048;          // 11-bit radix digits
 
 // TF CombinedNMS IOU on corner-normalised boxes with precomputed areas; returns iou > thr.
@@ -126,11 +127,14 @@ struct NmsShared {
 constexpr size_t kNmsSharedBytes = (sizeof(NmsShared) + 15) / 16 * 16;
 
 // One persistent CTA per (image, class) segment.
-//   loop over chunks of the candidate list in (score desc, index asc) order:
+//   loop over REFILLS of the candidate list in (score desc, index asc) order:
 //     SELECT   11-bit MSD radix select over the 64-bit composite (score key, ~index) finds a threshold that cuts
-//              off the next <= 512 unvisited candidates; whole histogram bins are accepted as soon as they give
-//              at least half a chunk, so unique scores need two histogram sweeps over the keys.
-//     COLLECT  + bitonic SORT of the chunk in shared memory, boxes staged (corner-normalised) with their areas.
+//              off the next <= 4096 unvisited candidates (all of pre_nms_top_n when that is smaller: the KITTI
+//              configuration selects its 2000 candidates ONCE); whole histogram bins are accepted as soon as they give
+//              at least half a list, so an open-ended list needs two histogram sweeps over the keys, an exact one three.
+//     COLLECT  + bitonic SORT of the list in shared memory (one select + one sort per refill instead of one per 512
+//              candidates: the sweeps over all N keys were 45 % of the kernel).
+//     per 1024-candidate sub-chunk of the sorted list: boxes staged (corner-normalised) with their areas, then
 //     GREEDY   64 candidates at a time: (a) all threads test the block against the kept list (shared memory,
 //              broadcast reads), (b) all threads build the 64x64 bitmask of the block, (c) one warp resolves the
 //              block with register bit operations and appends the survivors to the kept list.
@@ -142,8 +146,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // 8-byte items first, then 16-byte boxes, then 4-byte arrays: every sub-array stays naturally aligned for any cap
     NmsShared* S = reinterpret_cast<NmsShared*>(smem_raw);
-    unsigned long long* comp = reinterpret_cast<unsigned long long*>(smem_raw + kNmsSharedBytes);  // [kChunk]
-    float4* cbox = reinterpret_cast<float4*>(comp + kChunk);                                // [kChunk]
+    unsigned long long* comp = reinterpret_cast<unsigned long long*>(smem_raw + kNmsSharedBytes);  // [kList]
+    float4* cbox = reinterpret_cast<float4*>(comp + kList);                                 // [kChunk]
     float4* kbox = cbox + kChunk;                                                          // [cap]
     float* carea = reinterpret_cast<float*>(kbox + cap);                                    // [kChunk]
     float* karea = carea + kChunk;                                                         // [cap]
@@ -173,9 +177,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
             S->pfx = 0;
             S->pmask = 0;
             const int budget = S->budget;
-            // chunk target: 512 candidates when at most 512 boxes are kept (a select + sort round then costs about what
-            // its greedy blocks do), the full 1024 for larger caps (dense-anchor configurations need fewer rounds)
-            const int target = cap > kChunk / 2 ? kChunk : kChunk / 2;
+            // list target: everything pre_nms_top_n still allows, at most kList candidates per refill
+            const int target = kList;
             S->want_max = min(target, budget);
             // exact count only when pre_nms_top_n ends inside this chunk; otherwise any size in [half, full] will do
             S->want_min = budget <= target ? S->want_max : target / 2;
@@ -286,12 +289,12 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (take) {
                     const unsigned int pos = base + __popc(act & ((1u << lane) - 1u));
-                    if (pos < (unsigned)kChunk) comp[pos] = c;
+                    if (pos < (unsigned)kList) comp[pos] = c;
                 }
             }
         }
         __syncthreads();
-        const int m = min((int)S->cnt, kChunk);  // == expect by construction
+        const int m = min((int)S->cnt, kList);  // == expect by construction
         int p2 = 32;
         while (p2 < m) p2 <<= 1;
         for (int i = m + tid; i < p2; i += kNmsThreads) comp[i] = 0ull;
@@ -300,13 +303,13 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
         // ===================== SORT descending (bitonic network in shared memory) =======================
         for (int k = 2; k <= p2; k <<= 1) {
             for (int j = k >> 1; j > 0; j >>= 1) {
-                if (tid < p2) {
-                    const int ixj = tid ^ j;
-                    if (ixj > tid) {
-                        const unsigned long long a = comp[tid], b = comp[ixj];
-                        const bool desc = (tid & k) == 0;
+                for (int t = tid; t < p2; t += kNmsThreads) {
+                    const int ixj = t ^ j;
+                    if (ixj > t) {
+                        const unsigned long long a = comp[t], b = comp[ixj];
+                        const bool desc = (t & k) == 0;
                         if (desc ? (a < b) : (a > b)) {
-                            comp[tid] = b;
+                            comp[t] = b;
                             comp[ixj] = a;
                         }
                     }
@@ -315,9 +318,12 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
             }
         }
 
-        // ===================== LOAD boxes (corner-normalised) + areas ===================================
-        if (tid < m) {
-            const uint32_t idx = 0xffffffffu - (uint32_t)(comp[tid] & 0xffffffffull);
+      for (int sub = 0; sub < m && S->kept < cap; sub += kChunk) {  // (uniform: S->kept is written before a barrier)
+        const unsigned long long* scomp = comp + sub;
+        const int ms = min(kChunk, m - sub);
+        // ===================== LOAD boxes (corner-normalised) + areas of the sub-chunk ==================
+        if (tid < ms) {
+            const uint32_t idx = 0xffffffffu - (uint32_t)(scomp[tid] & 0xffffffffull);
             const float4 b = __ldg(sboxes + idx);
             const float4 nb4 = make_float4(fminf(b.x, b.z), fminf(b.y, b.w), fmaxf(b.x, b.z), fmaxf(b.y, b.w));
             cbox[tid] = nb4;
@@ -326,12 +332,12 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
         __syncthreads();
 
         // ===================== GREEDY, 64 candidates at a time ==========================================
-        const int nblk = (m + 63) / 64;
+        const int nblk = (ms + 63) / 64;
         for (int blk = 0; blk < nblk; ++blk) {
             const int kept = S->kept;  // uniform: written before the barrier that ended the previous block
             if (kept >= cap) break;
             const int base = blk * 64;
-            const int nvalid = min(64, m - base);
+            const int nvalid = min(64, ms - base);
             if (tid < 128) S->diag[tid] = 0u;
             if (tid < 2) S->dead[tid] = 0u;
             __syncthreads();
@@ -391,13 +397,15 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
                         const int pos = kept + __popcll(keepbits & ((1ull << i) - 1ull));
                         kbox[pos] = cbox[base + i];
                         karea[pos] = carea[base + i];
-                        sidx[pos] = (int32_t)(0xffffffffu - (uint32_t)(comp[base + i] & 0xffffffffull));
+                        sidx[pos] = (int32_t)(0xffffffffu - (uint32_t)(scomp[base + i] & 0xffffffffull));
                     }
                 }
                 if (lane == 0) S->kept = kept + __popcll(keepbits);
             }
             __syncthreads();
         }
+        __syncthreads();  // the next sub-chunk overwrites cbox / carea
+      }
         if (tid == 0) {
             S->hi = comp[m - 1];
             S->budget -= m;
@@ -425,7 +433,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
 }
 
 static size_t nms_smem_bytes(int cap) {
-    return sizeof(unsigned long long) * kChunk + sizeof(float4) * (kChunk + (size_t)cap) +
+    return sizeof(unsigned long long) * kList + sizeof(float4) * (kChunk + (size_t)cap) +
            sizeof(float) * (kChunk + (size_t)cap) + sizeof(unsigned int) * kBins + kNmsSharedBytes + 16;
 }
 

@@ -95,11 +95,9 @@ __global__ void __launch_bounds__(kPThreads, 1)
         const int roi_n = has_next ? idx_nxt / nch : 0, ch0_n = has_next ? (idx_nxt - roi_n * nch) * kWarpCh : 0;
         const int bin0 = roi * (kP * kP), bin0_n = roi_n * (kP * kP);
         const bool slow = cls == kClsGather || box >= kBwdNumBoxes - 1;  // no column inside the map, or wider than the ring
-        int W = 0;
-#pragma unroll
-        for (int i = 0; i < kBwdNumBoxes - 1; ++i) W = (box == i) ? box_width(i) : W;
+        const int row_bytes = (int)(uniform(lds_u32(rec + 180)) >> 16);  // tx_bytes of the record = W * 256: the forward's box
+        const int W = row_bytes / kPixBytes;
         const int nbufs = slow ? 1 : max(1, min(kBwdMaxBufs, kPBwdRowPix / max(W, 1)));
-        const int row_bytes = W * kPixBytes;
 
         int sy = 0;
         float yl_next = lds_f32(rec + 112);
@@ -203,8 +201,20 @@ __global__ void __launch_bounds__(kPThreads, 1)
                     __syncwarp();
                 }
                 const unsigned bufa = lane_s + rbuf_off;
-#pragma unroll 2
-                for (int p = 0; p < W; ++p) sts64(bufa + p * kPixBytes, 0ull);
+                {  // zero the W pixels of the buffer: four per iteration, then the remainder (W is 6 .. 26)
+                    int p = 0;
+#pragma unroll 1
+                    for (; p + 4 <= W; p += 4) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) sts64(bufa + (p + q) * kPixBytes, 0ull);
+                    }
+                    if (p + 2 <= W) {
+                        sts64(bufa + p * kPixBytes, 0ull);
+                        sts64(bufa + (p + 1) * kPixBytes, 0ull);
+                        p += 2;
+                    }
+                    if (p < W) sts64(bufa + p * kPixBytes, 0ull);
+                }
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     float wx[8];
@@ -221,7 +231,9 @@ __global__ void __launch_bounds__(kPThreads, 1)
                         const u64 lo = lds64(a), hi = lds64(a + kPixBytes);
                         sts64(a, fma2(G[i], pack2(xr, xr), lo));
                         sts64(a + kPixBytes, fma2(G[i], pack2(xl, xl), hi));
-                        G[i] = 0ull;
+                        // G - G = 0 in ONE packed instruction (ptxas turns a literal 64-bit zero into a uniform-register move
+                        // plus two copies, 56 instructions per flush; it cannot fold x - x for floats)
+                        asm volatile("sub.rn.f32x2 %0, %0, %0;" : "+l"(G[i]));
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the TMA engine
