@@ -48,7 +48,9 @@ struct __align__(16) RoiRecord {
     unsigned short slot_bytes, tx_bytes;    // 180 (W + first_px) * 256, W * 256
     unsigned char n_rows, box, first_px, cls, depth, n_before, n_after, pad0;  // 184
     unsigned short rows[2 * kS];            // 192 feature rows in the order the walk consumes them
-    unsigned char pad1[8];                  // 248
+    unsigned adv_mask;                      // 248 2 bits per crop column: how far the next column inside the map lies (0, 1, >= 2
+                                            //     pixels; the last one inside: 2; a column outside: 0) -- backward x-scatter
+    unsigned char mono, pad1[3];            // 252 1: the columns inside the map walk left to right (not a reversed box)
     // ---- second half: read from global memory by the gather path only (cls == kClsGather)
     unsigned short xlo[kS], xhi[kS], ylo[kS], yhi[kS];  // 256
     unsigned xok, yok;                      // 368 bit i: sample i lies inside the map
@@ -110,6 +112,12 @@ __global__ void __launch_bounds__(128) roi_records_kernel(const float4* __restri
     const unsigned prog_hi = __reduce_or_sync(all, (v && bitpos >= 32) ? (1u << (bitpos - 32)) : 0u);
     const int n_before = __popc(__ballot_sync(all, lane < kS && !v && !(mv & lt)));
     const unsigned xok = __ballot_sync(all, lane < kS && xs.ok), yok = mv;
+    // columns as the backward's x-scatter walks them: distance to the next column inside the map
+    const int lo_n = __shfl_down_sync(all, xs.lo, 1);
+    const bool ok_c = lane < kS && xs.ok, ok_n = lane + 1 < kS && ((xok >> (lane + 1)) & 1u);
+    const int adv = !ok_c ? 0 : !ok_n ? 2 : min(max(lo_n - xs.lo, 0), 2);
+    const unsigned adv_mask = __reduce_or_sync(all, lane < kS ? ((unsigned)adv << (2 * lane)) : 0u);
+    const bool mono = __all_sync(all, !(ok_c && ok_n) || lo_n >= xs.lo);
     if (lane < kS) {
         rec.aoff[lane] = xs.ok ? (xs.lo - sp.cmin + first_px) * kPixBytes : 0;
         rec.wx[lane] = xs.ok ? xs.lerp : 0.0f;
@@ -134,6 +142,8 @@ __global__ void __launch_bounds__(128) roi_records_kernel(const float4* __restri
         rec.n_before = (unsigned char)n_before;
         rec.n_after = (unsigned char)(kS - n_before - __popc(mv));
         rec.pad0 = 0;
+        rec.adv_mask = adv_mask;
+        rec.mono = mono ? 1 : 0;
         rec.xok = xok;
         rec.yok = yok;
         rec.b = b;

@@ -9,8 +9,10 @@
 //   * dY + codes arrive as a CONTINUOUS stream of bin-rows (7 bins x 64 channels + 7 x 16 code bytes per TMA pair) through
 //     a 3-slot ring that runs across item boundaries: while the last three bin-rows of an item are consumed, the first
 //     three of the next item are already in flight.
-//   * the x-scatter of a finished feature row is 14 straight-line read-modify-writes of a lane-private row buffer (a
-//     sample outside the map scatters with both weights 0), then one cp.reduce.async.bulk.tensor adds the row to dFeature.
+//   * the x-scatter of a finished feature row keeps the two pixels under the current sample in REGISTERS: the crop columns
+//     walk left to right, so a pixel is complete as soon as the walk moves past it and is stored once (the record says how
+//     far each column advances) -- no read-modify-write chain through shared memory.  One cp.reduce.async.bulk.tensor
+//     then adds the row buffer to dFeature.  Reversed boxes (and RoIs wider than the ring) take a plain atomic path.
 #pragma once
 
 constexpr int kPBwdRowPix = 28;                              // row-buffer ring of a warp, pixels
@@ -94,7 +96,9 @@ __global__ void __launch_bounds__(kPThreads, 1)
         const int roi = idx_cur / nch, ch0 = (idx_cur - roi * nch) * kWarpCh;
         const int roi_n = has_next ? idx_nxt / nch : 0, ch0_n = has_next ? (idx_nxt - roi_n * nch) * kWarpCh : 0;
         const int bin0 = roi * (kP * kP), bin0_n = roi_n * (kP * kP);
-        const bool slow = cls == kClsGather || box >= kBwdNumBoxes - 1;  // no column inside the map, or wider than the ring
+        const bool mono = (uniform(lds_u32(rec + 252)) & 0xffu) != 0u;
+        // no column inside the map, wider than the ring, or a reversed box (columns right to left): plain atomics
+        const bool slow = cls == kClsGather || box >= kBwdNumBoxes - 1 || !mono;
         const int row_bytes = (int)(uniform(lds_u32(rec + 180)) >> 16);  // tx_bytes of the record = W * 256: the forward's box
         const int W = row_bytes / kPixBytes;
         const int nbufs = slow ? 1 : max(1, min(kBwdMaxBufs, kPBwdRowPix / max(W, 1)));
@@ -170,6 +174,7 @@ __global__ void __launch_bounds__(kPThreads, 1)
                 okf[i] = outside ? 0.0f : 1.0f;
             }
             u64 prog = ((u64)uniform(lds_u32(rec + 176)) << 32) | uniform(lds_u32(rec + 172));
+            const unsigned adv_mask = uniform(lds_u32(rec + 248));
             u64 G0[kS], G1[kS];
 #pragma unroll
             for (int i = 0; i < kS; ++i) G0[i] = G1[i] = 0ull;
@@ -215,25 +220,37 @@ __global__ void __launch_bounds__(kPThreads, 1)
                     }
                     if (p < W) sts64(bufa + p * kPixBytes, 0ull);
                 }
+                {
+                    // the two pixels under the current sample live in registers; a pixel is stored once, when the walk has
+                    // moved past it (adv: 1 = one pixel on, 2 = both pixels done); same order of additions as the
+                    // read-modify-write form, so the same bits
+                    u64 acc_lo, acc_hi;
+                    asm volatile("mov.b64 %0, 0;" : "=l"(acc_lo));
+                    asm volatile("mov.b64 %0, 0;" : "=l"(acc_hi));
+                    float wx[16];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    float wx[8];
-#pragma unroll
-                    for (int q = 0; q < 2; ++q)
+                    for (int q = 0; q < 4; ++q)  // record bytes 0 .. 63: the 14 x weights
                         asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
                                      : "=f"(wx[4 * q]), "=f"(wx[4 * q + 1]), "=f"(wx[4 * q + 2]), "=f"(wx[4 * q + 3])
-                                     : "r"(rec + 32 * h + 16 * q));
+                                     : "r"(rec + 16 * q));
 #pragma unroll
-                    for (int i = 8 * h; i < (h ? kS : 8); ++i) {
-                        const float xl = wx[i - 8 * h];
+                    for (int i = 0; i < kS; ++i) {
+                        const float xl = wx[i];
                         const float xr = fsub(okf[i], xl);
-                        const unsigned a = (unsigned)aoff[i] + rbuf_off;
-                        const u64 lo = lds64(a), hi = lds64(a + kPixBytes);
-                        sts64(a, fma2(G[i], pack2(xr, xr), lo));
-                        sts64(a + kPixBytes, fma2(G[i], pack2(xl, xl), hi));
-                        // G - G = 0 in ONE packed instruction (ptxas turns a literal 64-bit zero into a uniform-register move
-                        // plus two copies, 56 instructions per flush; it cannot fold x - x for floats)
+                        acc_lo = fma2(G[i], pack2(xr, xr), acc_lo);
+                        acc_hi = fma2(G[i], pack2(xl, xl), acc_hi);
                         asm volatile("sub.rn.f32x2 %0, %0, %0;" : "+l"(G[i]));
+                        const unsigned m = (adv_mask >> (2 * i)) & 3u;  // warp-uniform
+                        if (m) {
+                            const unsigned a = (unsigned)aoff[i] + rbuf_off;
+                            sts64(a, acc_lo);
+                            if (m & 2u) {
+                                sts64(a + kPixBytes, acc_hi);
+                                asm volatile("sub.rn.f32x2 %0, %0, %0;" : "+l"(acc_hi));
+                            }
+                            acc_lo = acc_hi;
+                            asm volatile("sub.rn.f32x2 %0, %0, %0;" : "+l"(acc_hi));
+                        }
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the TMA engine

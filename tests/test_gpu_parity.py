@@ -860,3 +860,58 @@ def test_train_step_engine_matches_composed_calls_and_is_graph_capturable(det, o
         assert torch.equal(v, eager[k]), k
     # dFeature: TMA reduce-adds arrive in a different order on every run -> equal to rounding only
     assert float((eng.d_feature - eager["dfeat"]).abs().max()) <= 2e-5 * float(eager["dfeat"].abs().max())
+
+
+# ------------------------------------------------------------------ round-2 API additions
+def test_host_pipeline_submit_wait_two_batches_in_flight(det, orc, syn):
+    """frcnn_pipeline_submit / _wait: two different batches in flight at once (double-buffered device and host buffers,
+    C = 512: the persistent row-streaming kernels with one workspace per image) give exactly what separate runs give."""
+    w, anchors, scores, deltas, _ = _decoded(orc, syn, "kitti_b8", 4, 12)
+    f = syn.feature_maps(np.random.default_rng(8), 4, w.grid, 512)
+    pipe = det.ProposalRoIPipeline(w.image_shape, 2, w.grid, 512, w.num_anchors, 0.0, 0.7, 300, pre_nms_top_n=2000)
+    ref = []
+    for h in range(2):
+        out = pipe(anchors, scores[2 * h:2 * h + 2], deltas[2 * h:2 * h + 2], f[2 * h:2 * h + 2])
+        ref.append([t.clone() for t in out])
+    oref = orc.roi_pool_forward(f[:2], ref[0][0].numpy(), 7, 2)
+    np.testing.assert_array_equal(ref[0][3].numpy(), oref)
+    for rep in range(3):  # submit both, then wait in order; repeated so both device slots are reused
+        t0 = pipe.submit(anchors, scores[:2], deltas[:2], f[:2])
+        t1 = pipe.submit(anchors, scores[2:], deltas[2:], f[2:])
+        o0 = [t.clone() for t in pipe.wait(t0)]
+        o1 = [t.clone() for t in pipe.wait(t1)]
+        for got, want in ((o0, ref[0]), (o1, ref[1])):
+            for a, b in zip(got, want):
+                assert torch.equal(a, b), rep
+    pipe.close()
+
+
+def test_roi_pool_sm_budget_and_workspace_contract(det, orc, syn, rng):
+    """frcnn_roi_pool_set_max_sms: the persistent kernels give the same bits on 1, 7 or all SMs (dynamic item queue);
+    the row-streaming shapes refuse a missing / short workspace instead of running without their records."""
+    L = det._lib.load()
+    f = syn.feature_maps(rng, 2, (24, 78), 512)
+    rois = syn.random_rois(rng, 2, 40, num_valid=[37, 40])
+    ref = orc.roi_pool_forward(f, rois, 7, 2)
+    dy = rng.standard_normal(ref.shape).astype(F)
+    gref = orc.roi_pool_backward(f, rois, dy, 7, 2)
+    try:
+        for sms in (1, 7, 0):
+            assert L.frcnn_roi_pool_set_max_sms(sms) == 0
+            out, codes = det.roi_pool_forward_argmax(dev(f), dev(rois), 7, 2)
+            np.testing.assert_array_equal(host(out), ref)
+            np.testing.assert_array_equal(host(det.roi_pool_forward(dev(f), dev(rois), 7, 2)), ref)
+            g = host(det.roi_pool_backward_argmax(f.shape, dev(rois), dev(dy), codes, 7, 2))
+            np.testing.assert_allclose(g, gref, rtol=RTOL, atol=RTOL * np.abs(gref).max())
+    finally:
+        L.frcnn_roi_pool_set_max_sms(0)
+    need = L.frcnn_roi_pool_workspace_bytes(2, 40, 512, 7, 2)
+    assert need >= 256 + 512 * 80 and L.frcnn_roi_pool_workspace_bytes(2, 40, 64, 7, 2) == 0  # C = 64: bin-row walk, no records
+    ft, rt = dev(f), dev(rois)
+    out = torch.empty((2, 40, 7, 7, 512), device="cuda")
+    ws = torch.empty(need - 512, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    rc = L.frcnn_roi_pool_forward(ft.data_ptr(), 2, 24, 78, 512, rt.data_ptr(), 40, 7, 2, out.data_ptr(), ws.data_ptr(), need - 512, stream)
+    assert rc == -2 and "workspace" in det._lib.last_error()  # FRCNN_EWORKSPACE
+    rc = L.frcnn_roi_pool_forward(ft.data_ptr(), 2, 24, 78, 512, rt.data_ptr(), 40, 7, 2, out.data_ptr(), None, 0, stream)
+    assert rc == -2
