@@ -34,18 +34,14 @@ __device__ __forceinline__ void axis_sample(float c1, float c2, int extent, int 
 
 // Row-streaming forward for pooled_size 7 / kernel_size 2 / C % 512 == 0 (roi_pool_stream.cu).
 bool roi_pool_stream_supported(int C, int P, int k);
+// Per-RoI records + warp-persistent pooling kernel; workspace = counter + records.
 // codes != nullptr: training forward, also writes the arg-max codes ([B,R,P,P,C/4] bytes).
-int launch_roi_pool_fwd_stream(const float* feat, int B, int Hf, int Wf, int C, const float* rois, int R, float* out,
-                               unsigned char* codes, cudaStream_t st);
-// Persistent form (the one the library uses): per-RoI records + warp-persistent pooling kernel; workspace = counter + records.
 size_t roi_pool_stream_workspace_bytes(int B, int R);
 void roi_pool_set_max_sms(int max_sms);
 int launch_roi_pool_fwd_persist(const float* feat, int B, int Hf, int Wf, int C, const float* rois, int R, float* out,
                                 unsigned char* codes, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
 // Backward from the saved arg-max codes on the same walk (TMA reduce-add rows); dfeat must already be zeroed.
-int launch_roi_pool_bwd_stream(int B, int Hf, int Wf, int C, const float* rois, int R, const float* dy,
-                               const unsigned char* codes, float* dfeat, cudaStream_t st);
 
 int launch_roi_pool_bwd_persist(int B, int Hf, int Wf, int C, const float* rois, int R, const float* dy,
                                 const unsigned char* codes, float* dfeat, void* workspace, size_t workspace_bytes, cudaStream_t st);

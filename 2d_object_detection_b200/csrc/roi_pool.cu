@@ -19,17 +19,6 @@ constexpr bool kForceBinRowWalk = true;
 #else
 constexpr bool kForceBinRowWalk = false;
 #endif
-// FRCNN_DEFINES=FRCNN_AB_LEGACY_STREAM_FWD: the round-1 per-CTA streaming forward instead of the persistent one (A/B only).
-#ifdef FRCNN_AB_LEGACY_STREAM_FWD
-constexpr bool kLegacyStreamForward = true;
-#else
-constexpr bool kLegacyStreamForward = false;
-#endif
-#ifdef FRCNN_AB_LEGACY_STREAM_BWD
-constexpr bool kLegacyStreamBackward = true;
-#else
-constexpr bool kLegacyStreamBackward = false;
-#endif
 
 // ---- tiny vector abstraction: float4 (C % 4 == 0) or float -------------------------------------
 __device__ __forceinline__ float4 vload(const float4* p) { return __ldg(p); }
@@ -800,10 +789,7 @@ int frcnn_roi_pool_forward(const float* feat, int B, int Hf, int Wf, int C, cons
     if (R == 0) return 0;
     const dim3 grid(R, B);
     if (roi_pool_stream_supported(C, P, k) && !kForceBinRowWalk)
-        return kLegacyStreamForward
-                   ? launch_roi_pool_fwd_stream(feat, B, Hf, Wf, C, rois, R, out, nullptr, as_stream(stream))
-                   : launch_roi_pool_fwd_persist(feat, B, Hf, Wf, C, rois, R, out, nullptr, workspace, workspace_bytes,
-                                                 as_stream(stream));
+        return launch_roi_pool_fwd_persist(feat, B, Hf, Wf, C, rois, R, out, nullptr, workspace, workspace_bytes, as_stream(stream));
     if (C % 4 == 0 && k == 2 && (int64_t)Hf * Wf * (C / 4) < (1ll << 31)) {
         const int cv = C / 4;
         if (cv % 256 == 0)
@@ -872,10 +858,8 @@ int frcnn_roi_pool_forward_argmax(const float* feat, int B, int Hf, int Wf, int 
                   "roi_pool_forward_argmax: pointers must be 16-byte aligned");
     if (R == 0) return 0;
     if (roi_pool_stream_supported(C, P, k) && !kForceBinRowWalk)
-        return kLegacyStreamForward
-                   ? launch_roi_pool_fwd_stream(feat, B, Hf, Wf, C, rois, R, out, argmax_codes, as_stream(stream))
-                   : launch_roi_pool_fwd_persist(feat, B, Hf, Wf, C, rois, R, out, argmax_codes, workspace, workspace_bytes,
-                                                 as_stream(stream));
+        return launch_roi_pool_fwd_persist(feat, B, Hf, Wf, C, rois, R, out, argmax_codes, workspace, workspace_bytes,
+                                           as_stream(stream));
     return launch_codes<0>(feat, B, Hf, Wf, C, rois, R, P, out, argmax_codes, nullptr, nullptr, as_stream(stream));
 }
 
@@ -890,10 +874,8 @@ int frcnn_roi_pool_backward_argmax(int B, int Hf, int Wf, int C, const float* ro
     FRCNN_CUDA(cudaMemsetAsync(dfeat, 0, sizeof(float) * (size_t)B * Hf * Wf * C, as_stream(stream)));
     if (R == 0) return 0;
     if (roi_pool_stream_supported(C, P, k) && !kForceBinRowWalk)
-        return kLegacyStreamBackward
-                   ? launch_roi_pool_bwd_stream(B, Hf, Wf, C, rois, R, dy, argmax_codes, dfeat, as_stream(stream))
-                   : launch_roi_pool_bwd_persist(B, Hf, Wf, C, rois, R, dy, argmax_codes, dfeat, workspace, workspace_bytes,
-                                                 as_stream(stream));
+        return launch_roi_pool_bwd_persist(B, Hf, Wf, C, rois, R, dy, argmax_codes, dfeat, workspace, workspace_bytes,
+                                           as_stream(stream));
     return launch_codes<1>(nullptr, B, Hf, Wf, C, rois, R, P, nullptr, const_cast<unsigned char*>(argmax_codes), dy, dfeat,
                            as_stream(stream));
 }

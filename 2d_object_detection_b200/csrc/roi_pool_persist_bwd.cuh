@@ -239,6 +239,8 @@ __global__ void __launch_bounds__(kPThreads, 1)
                         const float xr = fsub(okf[i], xl);
                         acc_lo = fma2(G[i], pack2(xr, xr), acc_lo);
                         acc_hi = fma2(G[i], pack2(xl, xl), acc_hi);
+                        // G - G = 0 in ONE packed instruction (a literal zero here becomes a uniform-register move plus two copies;
+                        // ptxas cannot fold x - x for floats)
                         asm volatile("sub.rn.f32x2 %0, %0, %0;" : "+l"(G[i]));
                         const unsigned m = (adv_mask >> (2 * i)) & 3u;  // warp-uniform
                         if (m) {
@@ -246,10 +248,11 @@ __global__ void __launch_bounds__(kPThreads, 1)
                             sts64(a, acc_lo);
                             if (m & 2u) {
                                 sts64(a + kPixBytes, acc_hi);
-                                asm volatile("sub.rn.f32x2 %0, %0, %0;" : "+l"(acc_hi));
+                                acc_lo = 0ull;
+                            } else {
+                                acc_lo = acc_hi;
                             }
-                            acc_lo = acc_hi;
-                            asm volatile("sub.rn.f32x2 %0, %0, %0;" : "+l"(acc_hi));
+                            acc_hi = 0ull;
                         }
                     }
                 }
