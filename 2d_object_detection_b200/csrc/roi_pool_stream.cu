@@ -312,6 +312,8 @@ __device__ __forceinline__ void bwd_crop_row(u64 (&G0)[kS], u64 (&G1)[kS], bool 
         const unsigned mx = 3u << (4 * j), my = 12u << (4 * j);
         const u64 g0 = pack2((c0 & mx) == 0u ? d.x : 0.0f, (c0 & my) == 0u ? d.y : 0.0f);
         const u64 g1 = pack2((c1 & mx) == 0u ? d.x : 0.0f, (c1 & my) == 0u ? d.y : 0.0f);
+        // (ptxas writes half of these results into the dying gradient registers and copies them back into the accumulators
+        // -- 28 moves per crop row; neither the operand order nor a tied "+l" operand changes its choice)
         G0[2 * j] = fma2(g0, w0, G0[2 * j]);
         G1[2 * j] = fma2(g0, w1, G1[2 * j]);
         G0[2 * j + 1] = fma2(g1, w0, G0[2 * j + 1]);
