@@ -546,7 +546,8 @@ def measure_train(ctx, w, syn, steps, warmup, min_seconds):
     a, b = timed(max(3, min(steps, 10)))
     torch.cuda.synchronize()
     est = a.elapsed_time(b) / max(3, min(steps, 10))
-    n = int(max(steps, np.ceil(min_seconds * 1e3 / max(est, 1e-3))))
+    # every rank must run the SAME number of steps (each step holds an all-reduce): agree on the count
+    n = int(ctx.vmax(float(max(steps, np.ceil(min_seconds * 1e3 / max(est, 1e-3))))))
     sampler = ClockSampler(ctx.local_rank)
     a, b = timed(n)
     poll_until(b, sampler)

@@ -283,9 +283,9 @@ def test_roi_pool_forward_bit_exact(det, orc, syn, rng, grid, C, R, relu):
 
 @pytest.mark.parametrize("grid,C", [((24, 78), 1024), ((50, 84), 512), ((9, 11), 512), ((3, 2), 1536), ((1, 1), 512)])
 def test_roi_pool_forward_row_streaming_edge_cases(det, orc, syn, rng, grid, C):
-    """C % 512 == 0 with the 7x7 / k=2 configuration takes the row-streaming TMA kernel: every box width class, the zero
+    """C % 512 == 0 with the 7x7 / k=2 configuration takes the persistent row-streaming TMA kernel: every box width class, the zero
     pixel for samples outside the map, reversed boxes, RoIs wider than the ring (plain gather path), degenerate boxes,
-    1-pixel maps -- all bit-exact against the oracle, and identical to the older bin-row walk (FRCNN_FWD_WALK)."""
+    1-pixel maps -- all bit-exact against the oracle."""
     f = syn.feature_maps(rng, 2, grid, C, relu=False)
     R = 64
     rois = syn.random_rois(rng, 2, R, num_valid=[R - 3, R])
