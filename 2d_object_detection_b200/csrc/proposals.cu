@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
     __syncthreads();
 
     const int n_rounds = (N + kNmsThreads - 1) / kNmsThreads;
+    const bool vec4 = (reinterpret_cast<uintptr_t>(skeys) & 15u) == 0;  // this segment's keys allow 128-bit loads
 
     while (true) {
         // ===================== SELECT ===================================================================
@@ -198,21 +199,26 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
             for (int i = tid; i < nb; i += kNmsThreads) hist[i] = 0;
             __syncthreads();
             const unsigned long long pfx = S->pfx, pmask = S->pmask;
-            for (int r = 0; r < n_rounds; ++r) {
-                const int n = r * kNmsThreads + tid;
-                bool part = false;
-                unsigned int digit = 0;
-                if (n < N) {
-                    const uint32_t k = skeys[n];
-                    const unsigned long long c = composite(k, (uint32_t)n);
-                    part = (k != 0u) && (c < hi) && ((c & pmask) == pfx);
-                    digit = (unsigned int)(c >> shift) & (unsigned int)(nb - 1);
+            // one histogram sweep over the keys: 128-bit loads (four keys per thread and iteration, independent of each
+            // other, so the loads of a thread overlap) and one fire-and-forget shared-memory atomic per participating key --
+            // the match_any aggregation it replaces cost more than the bank conflicts it avoided (4.7 us per sweep)
+            auto count_key = [&](uint32_t k, int n) {
+                const unsigned long long c = composite(k, (uint32_t)n);
+                if ((k != 0u) && (c < hi) && ((c & pmask) == pfx))
+                    atomicAdd(&hist[(unsigned int)(c >> shift) & (unsigned int)(nb - 1)], 1u);
+            };
+            if (vec4) {
+                const uint4* k4 = reinterpret_cast<const uint4*>(skeys);
+                for (int v = tid; v < N / 4; v += kNmsThreads) {
+                    const uint4 q = k4[v];
+                    count_key(q.x, 4 * v);
+                    count_key(q.y, 4 * v + 1);
+                    count_key(q.z, 4 * v + 2);
+                    count_key(q.w, 4 * v + 3);
                 }
-                const unsigned act = __ballot_sync(0xffffffffu, part);
-                if (part) {  // warp-aggregated histogram update: one shared atomic per distinct digit
-                    const unsigned peers = __match_any_sync(act, digit);
-                    if (lane == __ffs(peers) - 1) atomicAdd(&hist[digit], (unsigned int)__popc(peers));
-                }
+                for (int n = (N / 4) * 4 + tid; n < N; n += kNmsThreads) count_key(skeys[n], n);
+            } else {
+                for (int n = tid; n < N; n += kNmsThreads) count_key(skeys[n], n);
             }
             __syncthreads();
             if (warp == 0) {
@@ -275,15 +281,10 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
         const unsigned long long thresh = S->thresh;
 
         // ===================== COLLECT the chunk (unordered) ===========================================
-        for (int r = 0; r < n_rounds; ++r) {
-            const int n = r * kNmsThreads + tid;
-            bool take = false;
-            unsigned long long c = 0;
-            if (n < N) {
-                const uint32_t k = skeys[n];
-                c = composite(k, (uint32_t)n);
-                take = (k != 0u) && (c < hi) && (c >= thresh);
-            }
+        // (uniform trip counts: every lane of a warp takes part in every ballot)
+        auto collect_key = [&](uint32_t k, int n, bool valid) {
+            const unsigned long long c = composite(k, (uint32_t)n);
+            const bool take = valid && (k != 0u) && (c < hi) && (c >= thresh);
             const unsigned act = __ballot_sync(0xffffffffu, take);
             if (act) {
                 unsigned int base = 0;
@@ -293,6 +294,28 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
                     const unsigned int pos = base + __popc(act & ((1u << lane) - 1u));
                     if (pos < (unsigned)kList) comp[pos] = c;
                 }
+            }
+        };
+        if (vec4) {
+            const uint4* k4 = reinterpret_cast<const uint4*>(skeys);
+            const int nv = N / 4, rounds4 = (nv + kNmsThreads - 1) / kNmsThreads;
+            for (int r = 0; r < rounds4; ++r) {
+                const int v = r * kNmsThreads + tid;
+                const bool valid = v < nv;
+                const uint4 q = valid ? k4[v] : make_uint4(0u, 0u, 0u, 0u);
+                collect_key(q.x, 4 * v, valid);
+                collect_key(q.y, 4 * v + 1, valid);
+                collect_key(q.z, 4 * v + 2, valid);
+                collect_key(q.w, 4 * v + 3, valid);
+            }
+            if (N & 3) {  // at most three keys behind the last full vector
+                const int n = nv * 4 + tid;
+                collect_key(n < N ? skeys[n] : 0u, n, n < N);
+            }
+        } else {
+            for (int r = 0; r < n_rounds; ++r) {
+                const int n = r * kNmsThreads + tid;
+                collect_key(n < N ? skeys[n] : 0u, n, n < N);
             }
         }
         __syncthreads();

@@ -46,7 +46,7 @@ struct __align__(16) RoiRecord {
     int pix0;                               // 168 b * Hf * Wf + cmin: TMA pixel coordinate of column cmin in feature row 0
     unsigned prog_lo, prog_hi;              // 172 the walk as a bit string (see StreamShared)
     unsigned short slot_bytes, tx_bytes;    // 180 (W + first_px) * 256, W * 256
-    unsigned char n_rows, box, first_px, cls, depth, n_before, n_after, big;  // 184 (big: listed in the front list, see below)
+    unsigned char n_rows, box, first_px, cls, depth, n_before, n_after, pad0;  // 184
     unsigned short rows[2 * kS];            // 192 feature rows in the order the walk consumes them
     unsigned adv_mask;                      // 248 2 bits per crop column: how far the next column inside the map lies (0, 1, >= 2
                                             //     pixels; the last one inside: 2; a column outside: 0) -- backward x-scatter
@@ -64,18 +64,9 @@ static_assert(offsetof(RoiRecord, wx) == 0 && offsetof(RoiRecord, aoff) == 56 &&
               "the kernel addresses record fields by offset");
 
 // One warp per RoI: the prologue of roi_pool_fwd_stream_kernel, once per RoI instead of once per (RoI, 256 channels) CTA.
-// Longest first: an item of a tall, wide RoI takes several times the average (it also starts cold and has a shallow
-// ring), and one that starts near the end of the kernel leaves the other SMs idle.  RoIs whose work estimate (feature rows x
-// slot pixels) reaches kBigWork are appended to a FRONT LIST (at most big_cap entries, one atomicAdd each) and flagged; the
-// pooling kernel hands the front list out first -- its items are exactly the static first items of the warps -- and skips
-// flagged RoIs when it meets them again in natural order.
-constexpr int kBigWork = 320;
-constexpr int kWsHeaderBytes = 2048;  // workspace: [0] work counter, [1] front-list length, bytes 1024..2047 front list (256 ints)
-constexpr int kBigListMax = 256;
-
 __global__ void __launch_bounds__(128) roi_records_kernel(const float4* __restrict__ rois, int n_rois, int R, int Hf, int Wf,
                                                           RoiRecord* __restrict__ recs, unsigned* __restrict__ counter,
-                                                          unsigned counter_init, int big_cap) {
+                                                          unsigned counter_init) {
     const int lane = threadIdx.x & 31, gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const unsigned all = 0xffffffffu;
     if (gw == 0 && lane == 0) *counter = counter_init;  // the work counter of the pooling kernel that follows on the stream
@@ -150,16 +141,7 @@ __global__ void __launch_bounds__(128) roi_records_kernel(const float4* __restri
         rec.depth = (unsigned char)(gather ? 1 : small ? min(kHalfDepth, kHalfPix / px) : max(1, min(kHalfDepth, kRingPix / px)));
         rec.n_before = (unsigned char)n_before;
         rec.n_after = (unsigned char)(kS - n_before - __popc(mv));
-        unsigned char big = 0;
-        const int work = gather ? (sp.need == 0 ? 0 : 4 * kBigWork) : (__popc(m1) + __popc(m2)) * px;
-        if (big_cap > 0 && work >= kBigWork) {  // (counter[1] was zeroed on the stream before this kernel)
-            const unsigned rank = atomicAdd(counter + 1, 1u);
-            if (rank < (unsigned)big_cap) {
-                reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(counter) + 1024)[rank] = gw;
-                big = 1;
-            }
-        }
-        rec.big = big;
+        rec.pad0 = 0;
         rec.adv_mask = adv_mask;
         rec.mono = mono ? 1 : 0;
         rec.xok = xok;
@@ -196,7 +178,7 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
 // The scalars of an item's record the walk keeps in (uniform) registers.
 struct PItem {
     unsigned rec;       // shared address of the record
-    int n_rows, depth, slot_bytes, tx_bytes, first_off, pix0, box, cls, big;
+    int n_rows, depth, slot_bytes, tx_bytes, first_off, pix0, box, cls;
     unsigned area;      // byte offset of the item's ring area inside the warp's ring (0 or half a ring)
     unsigned bar;       // index of the first row barrier of the item's set (0 or kHalfDepth)
 };
@@ -211,7 +193,6 @@ __device__ __forceinline__ PItem load_item(unsigned rec, int half) {
     it.first_off = (int)((f >> 16) & 0xffu) * kPixBytes;
     it.cls = (int)(f >> 24);
     it.depth = (int)(g & 0xffu);
-    it.big = (int)(g >> 24);
     it.pix0 = (int)uniform(lds_u32(rec + 168));
     const unsigned h = uniform((unsigned)half);  // (the caller's loop-carried flag, made provably warp-uniform)
     it.area = (it.cls == kClsSmall && h) ? (unsigned)(kHalfPix * kPixBytes) : 0u;
@@ -224,7 +205,7 @@ template <int kC, bool kCodes>
 __global__ void __launch_bounds__(kPThreads, 1)
     roi_pool_fwd_persist_kernel(const __grid_constant__ TensorMaps maps, const float* __restrict__ feat, int Hf, int Wf, int C_,
                                 const RoiRecord* __restrict__ recs, int n_items, float* __restrict__ out,
-                                unsigned char* __restrict__ codes, unsigned* __restrict__ counter, int big_cap) {
+                                unsigned char* __restrict__ codes, unsigned* __restrict__ counter) {
     const int C = kC ? kC : C_;
     const int nch = C / kWarpCh;  // 64-channel items per RoI
     extern __shared__ __align__(128) unsigned char smem[];
@@ -241,31 +222,18 @@ __global__ void __launch_bounds__(kPThreads, 1)
     const int total_warps = gridDim.x * kPWarps;
     int idx_cur = blockIdx.x * kPWarps + warp;  // the first two items are static; the counter starts at 2 * total_warps
     int idx_nxt = idx_cur + total_warps;
-    // Item numbering: [0, n_front) = the front list (big RoIs, longest first), then every RoI in natural order (flagged
-    // ones are skipped there).  n_front <= total_warps (big_cap), so only a warp's first static item can lie in the front.
-    const int* big_list = reinterpret_cast<const int*>(reinterpret_cast<const unsigned char*>(counter) + 1024);
-    const int n_front = min((int)uniform(lane == 0 ? counter[1] : 0u), big_cap) * nch;
-    const int n_total = n_front + n_items;
-    if (idx_cur >= n_total) return;
-    // RoI of an item.  Only a warp's FIRST item can come from the front list (looked up once, before the loop); every later
-    // item is in natural order, so the loop holds no load and all of its state stays provably warp-uniform.
-    int roi_first = 0;
-    if (idx_cur < n_front) roi_first = big_list[idx_cur / nch];
-    roi_first = (int)uniform((unsigned)roi_first);
-    const bool first_in_front = idx_cur < n_front;
-    auto roi_of = [&](int idx) { return (idx - n_front) / nch; };  // natural part
-    auto ch_of = [&](int idx) { return (idx % nch) * kWarpCh; };  // (n_front is a multiple of nch)
+    if (idx_cur >= n_items) return;
     const float onef = kOne;
     const u64 one = pack2(onef, onef);
 
-    auto fetch_record_of = [&](int roi, int buf) {  // (uniform arguments)
+    auto fetch_record = [&](int item, int buf) {  // (uniform arguments)
         if (lane == 0) {
             const unsigned bar = bar_s + (kRowBars + buf) * 8;
             mbar_expect_tx(bar, kRecBytes);
-            bulk_g2s(rec_s + buf * kRecBytes, reinterpret_cast<const unsigned char*>(recs) + (size_t)roi * kRecStride, kRecBytes, bar);
+            bulk_g2s(rec_s + buf * kRecBytes, reinterpret_cast<const unsigned char*>(recs) + (size_t)(item / nch) * kRecStride, kRecBytes,
+                     bar);
         }
     };
-    auto fetch_record = [&](int item, int buf) { fetch_record_of(roi_of(item), buf); };
     // Stage walk row k of an item into slot `slot` of its ring area: one TMA box, issued by one lane.
     auto stage = [&](const PItem& it, int ch0, int k, int slot) {
         if (lane == 0) {
@@ -286,8 +254,8 @@ __global__ void __launch_bounds__(kPThreads, 1)
     int buf = 0;                               // record buffer of the current item; the next item's is (buf + 1) % 3
     int half = 0;
     bool prefetched = false;
-    fetch_record_of(first_in_front ? roi_first : roi_of(idx_cur), 0);
-    if (idx_nxt < n_total) fetch_record(idx_nxt, 1);
+    fetch_record(idx_cur, 0);
+    if (idx_nxt < n_items) fetch_record(idx_nxt, 1);
     unsigned ticket = 0u;                      // lane 0: index of the item after next (an atomicAdd in flight)
     if (lane == 0) ticket = atomicAdd(counter, 1u);
     mbar_wait(bar_s + kRowBars * 8, 0u);       // the first record
@@ -296,16 +264,14 @@ __global__ void __launch_bounds__(kPThreads, 1)
 #pragma unroll 1
     for (;;) {
         const PItem it = load_item(rec_s + buf * kRecBytes, half);
-        const bool in_front = idx_cur < n_front;  // (only ever true in a warp's first iteration)
-        const int roi = in_front ? roi_first : roi_of(idx_cur), ch0 = ch_of(idx_cur);
-        const bool skip = it.big != 0 && !in_front;  // a front-list RoI met again in natural order: already done
-        if (!prefetched && !skip) stage_first_rows(it, ch0);  // cold start: nothing of this item is in flight yet
+        const int roi = idx_cur / nch, ch0 = (idx_cur - roi * nch) * kWarpCh;
+        if (!prefetched) stage_first_rows(it, ch0);  // cold start: nothing of this item is in flight yet
         // ---- look ahead: the item after next gets its record fetched, the next item (record already here) its first rows
         const int idx_n2 = (int)uniform(lane == 0 ? ticket : 0u);  // lane 0's ticket, broadcast into a uniform register
         const int nbuf = buf == kRecBufs - 1 ? 0 : buf + 1, n2buf = nbuf == kRecBufs - 1 ? 0 : nbuf + 1;
         bool next_prefetched = false;
-        if (idx_nxt < n_total) {
-            if (idx_n2 < n_total) {
+        if (idx_nxt < n_items) {
+            if (idx_n2 < n_items) {
                 fetch_record(idx_n2, n2buf);
                 if (lane == 0) ticket = atomicAdd(counter, 1u);
             }
@@ -313,8 +279,9 @@ __global__ void __launch_bounds__(kPThreads, 1)
             rec_phase ^= 1u << nbuf;
             if (it.cls == kClsSmall) {
                 const PItem nx = load_item(rec_s + nbuf * kRecBytes, half ^ 1);
-                if (nx.cls == kClsSmall && !(nx.big != 0 && idx_nxt >= n_front)) {  // (not for an item that will be skipped)
-                    stage_first_rows(nx, ch_of(idx_nxt));
+                if (nx.cls == kClsSmall) {
+                    const int nroi = idx_nxt / nch;
+                    stage_first_rows(nx, (idx_nxt - nroi * nch) * kWarpCh);
                     next_prefetched = true;
                 }
             }
@@ -324,9 +291,7 @@ __global__ void __launch_bounds__(kPThreads, 1)
         const int bin_stride = C / 2;  // float2 per bin
         unsigned char* cptr = kCodes ? codes + (size_t)roi * (kP * kP) * (C / 4) + (ch0 + lane * 2) / 4 : nullptr;
 
-        if (skip) {
-            // nothing to do: the look-ahead above keeps the record / ticket pipeline moving
-        } else if (it.cls == kClsGather) {
+        if (it.cls == kClsGather) {
             // rare (x-samples more than 51 columns apart, or no column inside the map): one bilinear gather per sample
             const RoiRecord& g = recs[roi];
             const float* fb = feat + (size_t)g.b * Hf * Wf * C + ch0 + lane * 2;
@@ -483,7 +448,7 @@ __global__ void __launch_bounds__(kPThreads, 1)
         // ---- next item
         idx_cur = (int)uniform((unsigned)idx_nxt);  // uniform loop exit: everything carried around the loop stays uniform
         idx_nxt = idx_n2;
-        if (idx_cur >= n_total) break;
+        if (idx_cur >= n_items) break;
         buf = nbuf;
         prefetched = uniform(next_prefetched ? 1u : 0u) != 0u;
         half = (int)uniform(next_prefetched ? (unsigned)(half ^ 1) : 0u);

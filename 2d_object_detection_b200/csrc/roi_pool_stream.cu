@@ -440,7 +440,7 @@ bool roi_pool_stream_supported(int C, int P, int k) { return C % 512 == 0 && C %
 static std::atomic<int> g_roi_pool_max_sms{0};
 void roi_pool_set_max_sms(int max_sms) { g_roi_pool_max_sms.store(max_sms > 0 ? max_sms : 0, std::memory_order_relaxed); }
 
-size_t roi_pool_stream_workspace_bytes(int B, int R) { return kWsHeaderBytes + (size_t)kRecStride * (size_t)B * (size_t)R; }
+size_t roi_pool_stream_workspace_bytes(int B, int R) { return 256 + (size_t)kRecStride * (size_t)B * (size_t)R; }
 
 // Persistent forward: records pre-kernel + warp-persistent pooling kernel.  workspace: [counter | records].
 int launch_roi_pool_fwd_persist(const float* feat, int B, int Hf, int Wf, int C, const float* rois, int R, float* out,
@@ -471,21 +471,19 @@ int launch_roi_pool_fwd_persist(const float* feat, int B, int Hf, int Wf, int C,
     const int rc = get_tensor_maps(feat, (long long)B * Hf * Wf, C, dev, &maps);
     if (rc) return rc;
     unsigned* counter = static_cast<unsigned*>(workspace);
-    RoiRecord* recs = reinterpret_cast<RoiRecord*>(static_cast<unsigned char*>(workspace) + kWsHeaderBytes);
-    const int n_rois = B * R, nch = C / kWarpCh, n_items = n_rois * nch;
+    RoiRecord* recs = reinterpret_cast<RoiRecord*>(static_cast<unsigned char*>(workspace) + 256);
+    const int n_rois = B * R, n_items = n_rois * (C / kWarpCh);
     const int budget = g_roi_pool_max_sms.load(std::memory_order_relaxed);
     const int ctas = min((n_items + kPWarps - 1) / kPWarps, budget > 0 ? min(budget, sms) : sms);  // one CTA per SM
-    const int big_cap = min(kBigListMax, ctas * kPWarps / nch);  // front-list items <= first static item of every warp
-    FRCNN_CUDA(cudaMemsetAsync(counter, 0, 8, st));                // work counter + front-list length
     roi_records_kernel<<<(n_rois + 3) / 4, 128, 0, st>>>((const float4*)rois, n_rois, R, Hf, Wf, recs, counter,
-                                                        2u * (unsigned)(ctas * kPWarps), big_cap);
+                                                        2u * (unsigned)(ctas * kPWarps));
     FRCNN_LAUNCH_CHECK("roi_records_kernel");
     if (codes) {
-        if (C == 1024) roi_pool_fwd_persist_kernel<1024, true><<<ctas, kPThreads, smem, st>>>(*maps, feat, Hf, Wf, C, recs, n_items, out, codes, counter, big_cap);
-        else roi_pool_fwd_persist_kernel<0, true><<<ctas, kPThreads, smem, st>>>(*maps, feat, Hf, Wf, C, recs, n_items, out, codes, counter, big_cap);
+        if (C == 1024) roi_pool_fwd_persist_kernel<1024, true><<<ctas, kPThreads, smem, st>>>(*maps, feat, Hf, Wf, C, recs, n_items, out, codes, counter);
+        else roi_pool_fwd_persist_kernel<0, true><<<ctas, kPThreads, smem, st>>>(*maps, feat, Hf, Wf, C, recs, n_items, out, codes, counter);
     } else {
-        if (C == 1024) roi_pool_fwd_persist_kernel<1024, false><<<ctas, kPThreads, smem, st>>>(*maps, feat, Hf, Wf, C, recs, n_items, out, nullptr, counter, big_cap);
-        else roi_pool_fwd_persist_kernel<0, false><<<ctas, kPThreads, smem, st>>>(*maps, feat, Hf, Wf, C, recs, n_items, out, nullptr, counter, big_cap);
+        if (C == 1024) roi_pool_fwd_persist_kernel<1024, false><<<ctas, kPThreads, smem, st>>>(*maps, feat, Hf, Wf, C, recs, n_items, out, nullptr, counter);
+        else roi_pool_fwd_persist_kernel<0, false><<<ctas, kPThreads, smem, st>>>(*maps, feat, Hf, Wf, C, recs, n_items, out, nullptr, counter);
     }
     FRCNN_LAUNCH_CHECK("roi_pool_fwd_persist_kernel");
     return 0;
@@ -518,12 +516,12 @@ int launch_roi_pool_bwd_persist(int B, int Hf, int Wf, int C, const float* rois,
     const int rc = get_bwd_maps(dfeat, (long long)B * Hf * Wf, dy, codes, (long long)B * R * kP * kP, C, dev, &maps);
     if (rc) return rc;
     unsigned* counter = static_cast<unsigned*>(workspace);
-    RoiRecord* recs = reinterpret_cast<RoiRecord*>(static_cast<unsigned char*>(workspace) + kWsHeaderBytes);
+    RoiRecord* recs = reinterpret_cast<RoiRecord*>(static_cast<unsigned char*>(workspace) + 256);
     const int n_rois = B * R, n_items = n_rois * (C / kWarpCh);
     const int budget = g_roi_pool_max_sms.load(std::memory_order_relaxed);
     const int ctas = min((n_items + kPWarps - 1) / kPWarps, budget > 0 ? min(budget, sms) : sms);
     roi_records_kernel<<<(n_rois + 3) / 4, 128, 0, st>>>((const float4*)rois, n_rois, R, Hf, Wf, recs, counter,
-                                                        2u * (unsigned)(ctas * kPWarps), /*big_cap=*/0);  // natural order
+                                                        2u * (unsigned)(ctas * kPWarps));
     FRCNN_LAUNCH_CHECK("roi_records_kernel");
     roi_pool_bwd_persist_kernel<<<ctas, kPThreads, smem, st>>>(*maps, Hf, Wf, C, recs, n_items, dy, codes, dfeat, counter);
     FRCNN_LAUNCH_CHECK("roi_pool_bwd_persist_kernel");
