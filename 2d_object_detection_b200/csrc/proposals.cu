@@ -120,6 +120,7 @@ struct NmsShared {
     unsigned long long thresh;    // chunk = eligible composites >= thresh
     int need, want_max, want_min, expect, kept, budget, remaining, stop, select_done;
     unsigned int cnt;
+    unsigned int wsum[32], wtotal; // block-wide scan of the histogram: candidates in the warps before a warp, all candidates
     unsigned int dead[2];         // per 64-block: candidates suppressed by already kept boxes
     unsigned int diag[128];       // per 64-block: 64x64 suppression bits among the block (row r: words 2r, 2r+1)
 };
@@ -221,27 +222,43 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
                 for (int n = tid; n < N; n += kNmsThreads) count_key(skeys[n], n);
             }
             __syncthreads();
-            if (warp == 0) {
-                const int per = nb / 32;
-                const int top_bin = nb - 1 - lane * per;  // lane 0 owns the highest digits
+            {   // Block-wide scan of the histogram in descending digit order (position p <-> digit nb - 1 - p): every thread
+                // sums its K digits, warp scans + one scan of the 32 warp totals give each thread the number of candidates
+                // above its digits; the one thread whose digits contain rank `need` decides.  (A single warp walking 64
+                // digits per lane did this before: as long as a sweep over the keys.)
+                int need = S->need;            // still wanted from inside the current prefix (read before anybody writes)
+                const int got = S->expect;     // already secured by bins above the current prefix
+                const int K = nb / kNmsThreads;  // 2 (11-bit digits) or 1 (10-bit digit of pass 2)
+                const int top_bin = nb - 1 - tid * K;
                 unsigned int sum = 0;
-                for (int q = 0; q < per; ++q) sum += hist[top_bin - q];
+                for (int q = 0; q < K; ++q) sum += hist[top_bin - q];
                 unsigned int incl = sum;
                 for (int o = 1; o < 32; o <<= 1) {
                     const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
                     if (lane >= o) incl += v;
                 }
-                const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
-                int need = S->need;            // still wanted from inside the current prefix
-                const int got = S->expect;     // already secured by bins above the current prefix
+                if (lane == 31) S->wsum[warp] = incl;
+                __syncthreads();
+                if (warp == 0) {
+                    const unsigned int w = S->wsum[lane];
+                    unsigned int wi = w;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned int v = __shfl_up_sync(0xffffffffu, wi, o);
+                        if (lane >= o) wi += v;
+                    }
+                    S->wsum[lane] = wi - w;  // candidates in the warps before this one
+                    if (lane == 31) S->wtotal = wi;
+                }
+                __syncthreads();
+                const unsigned int total = S->wtotal;
+                const unsigned int excl = S->wsum[warp] + incl - sum;
                 if (pass == 0) {               // total = all unvisited candidates of this segment
                     if ((int)total < need) need = (int)total;
-                    if (lane == 0) S->remaining = (int)total;
+                    if (tid == 0) S->remaining = (int)total;
                 }
-                const unsigned int excl = incl - sum;
-                if (need > 0 && excl < (unsigned)need && (unsigned)need <= incl) {  // exactly one lane
+                if (need > 0 && excl < (unsigned)need && (unsigned)need <= excl + sum) {  // exactly one thread
                     unsigned int cum = excl;
-                    for (int q = 0; q < per; ++q) {
+                    for (int q = 0; q < K; ++q) {
                         const unsigned int h = hist[top_bin - q];
                         if (cum + h >= (unsigned)need) {
                             const unsigned long long bin = (unsigned long long)(top_bin - q);
@@ -271,7 +288,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
                         cum += h;
                     }
                 }
-                if (need == 0 && lane == 0) S->select_done = 1;
+                if (need == 0 && tid == 0) S->select_done = 1;
             }
             __syncthreads();
             if (S->select_done) break;
