@@ -98,16 +98,39 @@ constexpr int kList = 4096;          // candidates selected + sorted per refill 
 constexpr int kBins = 2048;          // 11-bit radix digits
 
 // TF CombinedNMS IOU on corner-normalised boxes with precomputed areas; returns iou > thr.
-__device__ __forceinline__ bool tf_suppresses(const float4& a, float area_a, const float4& b, float area_b, float thr) {
-    float iou = 0.0f;
-    if (!(area_a <= 0.0f || area_b <= 0.0f)) {
-        const float d0 = fmaxf(fsub(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.0f);
-        const float d1 = fmaxf(fsub(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.0f);
-        const float inter = fmul(d0, d1);
-        if (inter == 0.0f && thr >= 0.0f) return false;  // 0 / positive = 0, never > thr
-        iou = fdiv(inter, fsub(fadd(area_a, area_b), inter));
+//
+// The exact rule divides: iou = inter / union (IEEE), compared with the threshold.  A warp tests 32 candidates against one
+// box and some lane nearly always overlaps it, so the division (and its divergent branch) ran for almost every test.  The
+// division is only needed when inter / union is within a few ulps of the threshold: with thr_lo = thr (1 - 2^-18) and
+// thr_hi = thr (1 + 2^-18), inter > thr_hi * union implies rn(inter / union) > thr and inter < thr_lo * union implies
+// rn(inter / union) < thr (the products and the quotient are each off by at most 2^-24 relative), so those two outcomes
+// are decided with one multiplication each and only the sliver in between takes the exact path.  NmsThreshold::make
+// disables the shortcut (thr_lo = -inf, thr_hi = +inf) for thresholds below 2^-10, negative or non-finite.
+struct NmsThreshold {
+    float thr, lo, hi;
+    __device__ static NmsThreshold make(float thr) {
+        NmsThreshold t{thr, -INFINITY, INFINITY};
+        if (thr >= 0.0009765625f && thr <= 1.0e6f) {
+            t.lo = fmul(thr, 1.0f - 3.814697265625e-6f);
+            t.hi = fmul(thr, 1.0f + 3.814697265625e-6f);
+        }
+        return t;
     }
-    return iou > thr;
+};
+__device__ __forceinline__ bool tf_suppresses(const float4& a, float area_a, const float4& b, float area_b, const NmsThreshold& t) {
+    const float d0 = fmaxf(fsub(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.0f);
+    const float d1 = fmaxf(fsub(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.0f);
+    const float inter = fmul(d0, d1);
+    const float uni = fsub(fadd(area_a, area_b), inter);
+    const bool valid = area_a > 0.0f && area_b > 0.0f && uni >= 1.0e-30f;  // (normal products: the error bounds hold)
+    if (valid && inter > fmul(t.hi, uni)) return true;
+    if (valid && inter < fmul(t.lo, uni)) return false;  // (includes inter == 0)
+    float iou = 0.0f;  // exact rule: degenerate boxes, NaNs, and quotients within 2^-18 of the threshold
+    if (!(area_a <= 0.0f || area_b <= 0.0f)) {
+        if (inter == 0.0f && t.thr >= 0.0f) return false;  // 0 / positive = 0, never > thr
+        iou = fdiv(inter, uni);
+    }
+    return iou > t.thr;
 }
 
 __device__ __forceinline__ uint64_t composite(uint32_t key, uint32_t idx) {
@@ -168,7 +191,20 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
     }
     int flag_exhausted = 0;
     __syncthreads();
+#ifdef FRCNN_NMS_TIMING  // debug build: time spent per phase (block 0, thread 0; printed at the end)
+    long long t_mark = clock64(), t_phase[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int n_chunks = 0, n_blocks = 0;
+#define NMS_TICK(i)                                   \
+    do {                                              \
+        const long long t_now__ = clock64();          \
+        t_phase[i] += t_now__ - t_mark;               \
+        t_mark = t_now__;                             \
+    } while (0)
+#else
+#define NMS_TICK(i) do { } while (0)
+#endif
 
+    const NmsThreshold nthr = NmsThreshold::make(iou_thr);
     const int n_rounds = (N + kNmsThreads - 1) / kNmsThreads;
     const bool vec4 = (reinterpret_cast<uintptr_t>(skeys) & 15u) == 0;  // this segment's keys allow 128-bit loads
 
@@ -294,6 +330,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
             if (S->select_done) break;
         }
         const int expect = S->expect;
+        NMS_TICK(0);
         if (expect == 0) break;  // no candidates left (uniform)
         const unsigned long long thresh = S->thresh;
 
@@ -342,9 +379,13 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
         for (int i = m + tid; i < p2; i += kNmsThreads) comp[i] = 0ull;
         __syncthreads();
 
-        // ===================== SORT descending (bitonic network in shared memory) =======================
+        NMS_TICK(1);
+        // ===================== SORT descending (bitonic network) ========================================
+        // Exchanges at distance >= 32 go through shared memory (one barrier each); the distances 16 .. 1 that end every
+        // phase stay inside a warp and run on registers with shuffles -- 19 barriers instead of 45 for 512 candidates.
         for (int k = 2; k <= p2; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
+            int j = k >> 1;
+            for (; j >= 32; j >>= 1) {
                 for (int t = tid; t < p2; t += kNmsThreads) {
                     const int ixj = t ^ j;
                     if (ixj > t) {
@@ -358,8 +399,20 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
                 }
                 __syncthreads();
             }
+            for (int t = tid; t < p2; t += kNmsThreads) {  // (p2 is a multiple of 32: whole warps take part)
+                unsigned long long v = comp[t];
+                const bool desc = (t & k) == 0;
+                for (int jj = j; jj > 0; jj >>= 1) {
+                    const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, jj);
+                    const bool keep_max = (((t & jj) == 0) == desc);  // the lower index of a descending pair keeps the larger
+                    v = keep_max ? (v > o ? v : o) : (v < o ? v : o);
+                }
+                comp[t] = v;
+            }
+            __syncthreads();
         }
 
+        NMS_TICK(2);
       for (int sub = 0; sub < m && S->kept < cap; sub += kChunk) {  // (uniform: S->kept is written before a barrier)
         const unsigned long long* scomp = comp + sub;
         const int ms = min(kChunk, m - sub);
@@ -373,6 +426,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
         }
         __syncthreads();
 
+        NMS_TICK(3);
         // ===================== GREEDY, 64 candidates at a time ==========================================
         const int nblk = (ms + 63) / 64;
         for (int blk = 0; blk < nblk; ++blk) {
@@ -383,6 +437,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
             if (tid < 128) S->diag[tid] = 0u;
             if (tid < 2) S->dead[tid] = 0u;
             __syncthreads();
+            NMS_TICK(5);
             {   // (a) block vs kept list: thread = (candidate, one of 16 interleaved slices of the kept list)
                 const int cand = tid & 63, part = tid >> 6;
                 if (cand < nvalid && part < kept) {
@@ -390,7 +445,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
                     const float at = carea[base + cand];
                     bool sup = false;
                     for (int j = part; j < kept; j += kNmsThreads / 64) {
-                        if (tf_suppresses(bt, at, kbox[j], karea[j], iou_thr)) {
+                        if (tf_suppresses(bt, at, kbox[j], karea[j], nthr)) {
                             sup = true;
                             break;
                         }
@@ -407,31 +462,41 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const int u = 4 * g + q;
-                        if (u > row && u < nvalid && tf_suppresses(bt, at, cbox[base + u], carea[base + u], iou_thr))
+                        if (u > row && u < nvalid && tf_suppresses(bt, at, cbox[base + u], carea[base + u], nthr))
                             bits |= 1u << q;
                     }
                     if (bits) atomicOr(&S->diag[2 * row + (g >> 3)], bits << ((4 * g) & 31));
                 }
             }
+            NMS_TICK(6);
             __syncthreads();
-            if (warp == 0) {  // (c) resolve: lane l holds the mask rows l and l+32
+            NMS_TICK(7);
+            if (warp == 0) {  // (c) resolve: lane l holds the mask rows l and l+32, as 32-bit words (row r only has bits > r)
                 const unsigned long long valid = nvalid == 64 ? ~0ull : ((1ull << nvalid) - 1ull);
-                unsigned long long cur = ((unsigned long long)S->dead[0] | ((unsigned long long)S->dead[1] << 32)) | ~valid;
-                const unsigned long long d0 = (unsigned long long)S->diag[2 * lane] | ((unsigned long long)S->diag[2 * lane + 1] << 32);
-                const unsigned long long d1 =
-                    (unsigned long long)S->diag[2 * (lane + 32)] | ((unsigned long long)S->diag[2 * (lane + 32) + 1] << 32);
-                unsigned long long keepbits = 0ull;
+                unsigned int cur_lo = S->dead[0] | ~(unsigned int)valid, cur_hi = S->dead[1] | ~(unsigned int)(valid >> 32);
+                const unsigned int r0_lo = S->diag[2 * lane], r0_hi = S->diag[2 * lane + 1], r1_hi = S->diag[2 * (lane + 32) + 1];
+                unsigned int keep_lo = 0u, keep_hi = 0u;
                 int room = cap - kept;
 #pragma unroll
-                for (int i = 0; i < 64; ++i) {
-                    const unsigned long long di = __shfl_sync(0xffffffffu, i < 32 ? d0 : d1, i & 31);
-                    const bool take = !((cur >> i) & 1ull) && room > 0;
-                    if (take) {
-                        keepbits |= 1ull << i;
-                        cur |= di;
+                for (int i = 0; i < 32; ++i) {
+                    const unsigned int lo = __shfl_sync(0xffffffffu, r0_lo, i), hi = __shfl_sync(0xffffffffu, r0_hi, i);
+                    if (!(cur_lo & (1u << i)) && room > 0) {
+                        keep_lo |= 1u << i;
+                        cur_lo |= lo;
+                        cur_hi |= hi;
                         --room;
                     }
                 }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const unsigned int hi = __shfl_sync(0xffffffffu, r1_hi, i);
+                    if (!(cur_hi & (1u << i)) && room > 0) {
+                        keep_hi |= 1u << i;
+                        cur_hi |= hi;
+                        --room;
+                    }
+                }
+                const unsigned long long keepbits = (unsigned long long)keep_lo | ((unsigned long long)keep_hi << 32);
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {  // append survivors (lane handles bits lane and lane+32)
                     const int i = lane + 32 * h;
@@ -445,8 +510,10 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
                 if (lane == 0) S->kept = kept + __popcll(keepbits);
             }
             __syncthreads();
+            NMS_TICK(8);
         }
         __syncthreads();  // the next sub-chunk overwrites cbox / carea
+        NMS_TICK(4);
       }
         if (tid == 0) {
             S->hi = comp[m - 1];
@@ -467,6 +534,12 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
     }
     __syncthreads();
     const int kept = S->kept;
+#ifdef FRCNN_NMS_TIMING
+    if (tid == 0 && blockIdx.x == 0)
+        printf("nms timing (cycles): select %lld collect %lld sort %lld load %lld greedy-rest %lld | per block: zero+bar %lld  a+b(thread 0) %lld  "
+               "bar %lld  resolve+bar %lld   kept %d\n", t_phase[0], t_phase[1], t_phase[2], t_phase[3], t_phase[4], t_phase[5], t_phase[6],
+               t_phase[7], t_phase[8], kept);
+#endif
     for (int i = kept + tid; i < cap; i += kNmsThreads) sidx[i] = -1;
     if (tid == 0) {
         kept_count[seg] = kept;
