@@ -96,6 +96,7 @@ constexpr int kNmsThreads = 1024;
 constexpr int kChunk = 1024;         // candidates whose boxes are staged + resolved at a time (sub-chunk of the sorted list)
 constexpr int kList = 4096;          // candidates selected + sorted per refill (a refill = one radix select over all N keys)
 constexpr int kBins = 2048;          // 11-bit radix digits
+constexpr int kHistCopies = 8;       // private copies of the radix histogram (warp & 7): the first digit has ~30 hot bins
 
 // TF CombinedNMS IOU on corner-normalised boxes with precomputed areas; returns iou > thr.
 //
@@ -205,7 +206,6 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
 #endif
 
     const NmsThreshold nthr = NmsThreshold::make(iou_thr);
-    const int n_rounds = (N + kNmsThreads - 1) / kNmsThreads;
     const bool vec4 = (reinterpret_cast<uintptr_t>(skeys) & 15u) == 0;  // this segment's keys allow 128-bit loads
 
     while (true) {
@@ -233,8 +233,9 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
             // digit layout: key bits 31..21, 20..10, 9..0 ; then ~idx bits 21..11, 10..0 (idx < 2^22)
             const int shift = pass == 0 ? 53 : pass == 1 ? 42 : pass == 2 ? 32 : pass == 3 ? 11 : 0;
             const int nb = pass == 2 ? 1024 : kBins;
-            for (int i = tid; i < nb; i += kNmsThreads) hist[i] = 0;
+            for (int i = tid; i < kHistCopies * kBins; i += kNmsThreads) hist[i] = 0;
             __syncthreads();
+            unsigned int* myhist = hist + (warp & (kHistCopies - 1)) * kBins;
             const unsigned long long pfx = S->pfx, pmask = S->pmask;
             // one histogram sweep over the keys: 128-bit loads (four keys per thread and iteration, independent of each
             // other, so the loads of a thread overlap) and one fire-and-forget shared-memory atomic per participating key --
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
             auto count_key = [&](uint32_t k, int n) {
                 const unsigned long long c = composite(k, (uint32_t)n);
                 if ((k != 0u) && (c < hi) && ((c & pmask) == pfx))
-                    atomicAdd(&hist[(unsigned int)(c >> shift) & (unsigned int)(nb - 1)], 1u);
+                    atomicAdd(&myhist[(unsigned int)(c >> shift) & (unsigned int)(nb - 1)], 1u);
             };
             if (vec4) {
                 const uint4* k4 = reinterpret_cast<const uint4*>(skeys);
@@ -266,8 +267,10 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
                 const int got = S->expect;     // already secured by bins above the current prefix
                 const int K = nb / kNmsThreads;  // 2 (11-bit digits) or 1 (10-bit digit of pass 2)
                 const int top_bin = nb - 1 - tid * K;
-                unsigned int sum = 0;
-                for (int q = 0; q < K; ++q) sum += hist[top_bin - q];
+                unsigned int hk[2] = {0u, 0u};  // this thread's digits, summed over the private copies
+                for (int q = 0; q < K; ++q)
+                    for (int cpy = 0; cpy < kHistCopies; ++cpy) hk[q] += hist[cpy * kBins + top_bin - q];
+                const unsigned int sum = hk[0] + hk[1];
                 unsigned int incl = sum;
                 for (int o = 1; o < 32; o <<= 1) {
                     const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -295,7 +298,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
                 if (need > 0 && excl < (unsigned)need && (unsigned)need <= excl + sum) {  // exactly one thread
                     unsigned int cum = excl;
                     for (int q = 0; q < K; ++q) {
-                        const unsigned int h = hist[top_bin - q];
+                        const unsigned int h = hk[q];
                         if (cum + h >= (unsigned)need) {
                             const unsigned long long bin = (unsigned long long)(top_bin - q);
                             unsigned long long npfx = pfx | (bin << shift);
@@ -335,42 +338,27 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
         const unsigned long long thresh = S->thresh;
 
         // ===================== COLLECT the chunk (unordered) ===========================================
-        // (uniform trip counts: every lane of a warp takes part in every ballot)
-        auto collect_key = [&](uint32_t k, int n, bool valid) {
+        // Only ~ one key in 30 is taken, so every taker simply reserves its slot with a shared-memory atomic (the order
+        // inside the list is irrelevant: it is sorted next); 128-bit key loads as in the histogram sweeps.
+        auto collect_key = [&](uint32_t k, int n) {
             const unsigned long long c = composite(k, (uint32_t)n);
-            const bool take = valid && (k != 0u) && (c < hi) && (c >= thresh);
-            const unsigned act = __ballot_sync(0xffffffffu, take);
-            if (act) {
-                unsigned int base = 0;
-                if (lane == 0) base = atomicAdd(&S->cnt, (unsigned int)__popc(act));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (take) {
-                    const unsigned int pos = base + __popc(act & ((1u << lane) - 1u));
-                    if (pos < (unsigned)kList) comp[pos] = c;
-                }
+            if ((k != 0u) && (c < hi) && (c >= thresh)) {
+                const unsigned int pos = atomicAdd(&S->cnt, 1u);
+                if (pos < (unsigned)kList) comp[pos] = c;
             }
         };
         if (vec4) {
             const uint4* k4 = reinterpret_cast<const uint4*>(skeys);
-            const int nv = N / 4, rounds4 = (nv + kNmsThreads - 1) / kNmsThreads;
-            for (int r = 0; r < rounds4; ++r) {
-                const int v = r * kNmsThreads + tid;
-                const bool valid = v < nv;
-                const uint4 q = valid ? k4[v] : make_uint4(0u, 0u, 0u, 0u);
-                collect_key(q.x, 4 * v, valid);
-                collect_key(q.y, 4 * v + 1, valid);
-                collect_key(q.z, 4 * v + 2, valid);
-                collect_key(q.w, 4 * v + 3, valid);
+            for (int v = tid; v < N / 4; v += kNmsThreads) {
+                const uint4 q = k4[v];
+                collect_key(q.x, 4 * v);
+                collect_key(q.y, 4 * v + 1);
+                collect_key(q.z, 4 * v + 2);
+                collect_key(q.w, 4 * v + 3);
             }
-            if (N & 3) {  // at most three keys behind the last full vector
-                const int n = nv * 4 + tid;
-                collect_key(n < N ? skeys[n] : 0u, n, n < N);
-            }
+            for (int n = (N / 4) * 4 + tid; n < N; n += kNmsThreads) collect_key(skeys[n], n);
         } else {
-            for (int r = 0; r < n_rounds; ++r) {
-                const int n = r * kNmsThreads + tid;
-                collect_key(n < N ? skeys[n] : 0u, n, n < N);
-            }
+            for (int n = tid; n < N; n += kNmsThreads) collect_key(skeys[n], n);
         }
         __syncthreads();
         const int m = min((int)S->cnt, kList);  // == expect by construction
@@ -549,7 +537,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
 
 static size_t nms_smem_bytes(int cap) {
     return sizeof(unsigned long long) * kList + sizeof(float4) * (kChunk + (size_t)cap) +
-           sizeof(float) * (kChunk + (size_t)cap) + sizeof(unsigned int) * kBins + kNmsSharedBytes + 16;
+           sizeof(float) * (kChunk + (size_t)cap) + sizeof(unsigned int) * kBins * kHistCopies + kNmsSharedBytes + 16;
 }
 
 // ------------------------------------------------------------------------------------------------
