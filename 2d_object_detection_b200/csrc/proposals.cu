@@ -96,7 +96,6 @@ constexpr int kNmsThreads = 1024;
 constexpr int kChunk = 1024;         // candidates whose boxes are staged + resolved at a time (sub-chunk of the sorted list)
 constexpr int kList = 4096;          // candidates selected + sorted per refill (a refill = one radix select over all N keys)
 constexpr int kBins = 2048;          // 11-bit radix digits
-constexpr int kHistCopies = 8;       // private copies of the radix histogram (warp & 7): the first digit has ~30 hot bins
 
 // TF CombinedNMS IOU on corner-normalised boxes with precomputed areas; returns iou > thr.
 //
@@ -233,17 +232,17 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
             // digit layout: key bits 31..21, 20..10, 9..0 ; then ~idx bits 21..11, 10..0 (idx < 2^22)
             const int shift = pass == 0 ? 53 : pass == 1 ? 42 : pass == 2 ? 32 : pass == 3 ? 11 : 0;
             const int nb = pass == 2 ? 1024 : kBins;
-            for (int i = tid; i < kHistCopies * kBins; i += kNmsThreads) hist[i] = 0;
+            for (int i = tid; i < nb; i += kNmsThreads) hist[i] = 0;
             __syncthreads();
-            unsigned int* myhist = hist + (warp & (kHistCopies - 1)) * kBins;
             const unsigned long long pfx = S->pfx, pmask = S->pmask;
             // one histogram sweep over the keys: 128-bit loads (four keys per thread and iteration, independent of each
             // other, so the loads of a thread overlap) and one fire-and-forget shared-memory atomic per participating key --
-            // the match_any aggregation it replaces cost more than the bank conflicts it avoided (4.7 us per sweep)
+            // the match_any aggregation it replaces cost more than the bank conflicts it avoided (4.7 us per sweep; eight
+            // private copies of the histogram were tried too: zeroing and summing them costs more than the conflicts)
             auto count_key = [&](uint32_t k, int n) {
                 const unsigned long long c = composite(k, (uint32_t)n);
                 if ((k != 0u) && (c < hi) && ((c & pmask) == pfx))
-                    atomicAdd(&myhist[(unsigned int)(c >> shift) & (unsigned int)(nb - 1)], 1u);
+                    atomicAdd(&hist[(unsigned int)(c >> shift) & (unsigned int)(nb - 1)], 1u);
             };
             if (vec4) {
                 const uint4* k4 = reinterpret_cast<const uint4*>(skeys);
@@ -267,9 +266,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
                 const int got = S->expect;     // already secured by bins above the current prefix
                 const int K = nb / kNmsThreads;  // 2 (11-bit digits) or 1 (10-bit digit of pass 2)
                 const int top_bin = nb - 1 - tid * K;
-                unsigned int hk[2] = {0u, 0u};  // this thread's digits, summed over the private copies
-                for (int q = 0; q < K; ++q)
-                    for (int cpy = 0; cpy < kHistCopies; ++cpy) hk[q] += hist[cpy * kBins + top_bin - q];
+                unsigned int hk[2] = {0u, 0u};  // this thread's digits
+                for (int q = 0; q < K; ++q) hk[q] = hist[top_bin - q];
                 const unsigned int sum = hk[0] + hk[1];
                 unsigned int incl = sum;
                 for (int o = 1; o < 32; o <<= 1) {
@@ -537,7 +535,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
 
 static size_t nms_smem_bytes(int cap) {
     return sizeof(unsigned long long) * kList + sizeof(float4) * (kChunk + (size_t)cap) +
-           sizeof(float) * (kChunk + (size_t)cap) + sizeof(unsigned int) * kBins * kHistCopies + kNmsSharedBytes + 16;
+           sizeof(float) * (kChunk + (size_t)cap) + sizeof(unsigned int) * kBins + kNmsSharedBytes + 16;
 }
 
 // ------------------------------------------------------------------------------------------------
