@@ -167,6 +167,14 @@ __device__ __forceinline__ unsigned lds_u16(unsigned addr) {
     return v;
 }
 __device__ __forceinline__ unsigned uniform(unsigned v) { return __reduce_or_sync(0xffffffffu, v); }  // warp-uniform -> uniform register
+// Next work item: a plain atom issued by ONE lane whose result is only read an item later.  (atomicAdd() under
+// `if (lane == 0)` is turned into the compiler's warp-aggregated form, which shuffles the result out at once and so waits
+// for the round trip to L2 on the spot: 3-4 % of the kernel's stall samples.)
+__device__ __forceinline__ unsigned take_ticket(unsigned* counter) {
+    unsigned t;
+    asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(counter) : "memory");
+    return t;
+}
 
 // 256-byte record, global -> shared, completion on `bar` (issued by one lane)
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
@@ -235,14 +243,14 @@ __global__ void __launch_bounds__(kPThreads, 1)
         }
     };
     // Stage walk row k of an item into slot `slot` of its ring area: one TMA box, issued by one lane.
-    auto stage = [&](const PItem& it, int ch0, int k, int slot) {
+    auto stage_row = [&](const PItem& it, int ch0, int row, int slot) {  // feature row `row` of the item's image
         if (lane == 0) {
-            const int row = (int)lds_u16(it.rec + 192 + 2 * k);
             const unsigned bar = bar_s + (it.bar + slot) * 8;
             mbar_expect_tx(bar, (unsigned)it.tx_bytes);
             tma_box_g2s(ring_s + it.area + slot * it.slot_bytes + it.first_off, &maps.box[it.box], ch0, it.pix0 + row * Wf, bar);
         }
     };
+    auto stage = [&](const PItem& it, int ch0, int k, int slot) { stage_row(it, ch0, (int)lds_u16(it.rec + 192 + 2 * k), slot); };
     auto stage_first_rows = [&](const PItem& it, int ch0) {
         if (it.cls == kClsGather) return;
         const int n = min(it.depth, it.n_rows);
@@ -257,7 +265,7 @@ __global__ void __launch_bounds__(kPThreads, 1)
     fetch_record(idx_cur, 0);
     if (idx_nxt < n_items) fetch_record(idx_nxt, 1);
     unsigned ticket = 0u;                      // lane 0: index of the item after next (an atomicAdd in flight)
-    if (lane == 0) ticket = atomicAdd(counter, 1u);
+    if (lane == 0) ticket = take_ticket(counter);
     mbar_wait(bar_s + kRowBars * 8, 0u);       // the first record
     rec_phase = 1u;
 
@@ -273,7 +281,7 @@ __global__ void __launch_bounds__(kPThreads, 1)
         if (idx_nxt < n_items) {
             if (idx_n2 < n_items) {
                 fetch_record(idx_n2, n2buf);
-                if (lane == 0) ticket = atomicAdd(counter, 1u);
+                if (lane == 0) ticket = take_ticket(counter);
             }
             mbar_wait(bar_s + (kRowBars + nbuf) * 8, (rec_phase >> nbuf) & 1u);  // fetched one item ago: normally complete
             rec_phase ^= 1u << nbuf;
@@ -353,6 +361,9 @@ __global__ void __launch_bounds__(kPThreads, 1)
             unsigned slot_off = it.area;
             // x-interpolate the next staged feature row into X, then re-arm its slot with row k + depth
             auto load_row = [&](u64(&X)[kS]) {
+                // (the feature row that will re-arm this slot: read from the record before the wait, so that the elected
+                // lane does not sit on the shared-memory latency when it builds the TMA coordinate)
+                const int next_row = (int)lds_u16(it.rec + 192 + 2 * (k + it.depth));
                 const unsigned bit = it.bar + slot;
                 mbar_wait(bar_s + bit * 8, (row_phase >> bit) & 1u);
                 row_phase ^= 1u << bit;
@@ -373,7 +384,7 @@ __global__ void __launch_bounds__(kPThreads, 1)
                     }
                 }
                 __syncwarp();  // every lane has consumed its operands: the slot may be overwritten
-                if (k + it.depth < it.n_rows) stage(it, ch0, k + it.depth, slot);
+                if (k + it.depth < it.n_rows) stage_row(it, ch0, next_row, slot);
                 ++k;
                 slot_off += it.slot_bytes;
                 if (++slot == it.depth) {
