@@ -167,9 +167,11 @@ __device__ __forceinline__ unsigned lds_u16(unsigned addr) {
     return v;
 }
 __device__ __forceinline__ unsigned uniform(unsigned v) { return __reduce_or_sync(0xffffffffu, v); }  // warp-uniform -> uniform register
-// Next work item: a plain atom issued by ONE lane whose result is only read an item later.  (atomicAdd() under
-// `if (lane == 0)` is turned into the compiler's warp-aggregated form, which shuffles the result out at once and so waits
-// for the round trip to L2 on the spot: 3-4 % of the kernel's stall samples.)
+// Next work item: one atom per item, issued by lane 0 two items ahead of its use.  ptxas turns every integer atom.add /
+// atom.inc (atomicAdd() and inline PTX alike) into its warp-aggregated form (VOTE / POPC / ATOMG / SHFL), which waits
+// for the round trip to L2 at the issue point: 3-4 % of the stall samples.  A float counter (atom.add.f32 is left
+// alone) removes that wait, but the time moves into the row-barrier waits: 0.1687 vs 0.1695 ms forward, 0.3434 vs
+// 0.3421 ms backward in an alternating A/B on one box -- not worth a 2^24-item limit, so the counter stays an integer.
 __device__ __forceinline__ unsigned take_ticket(unsigned* counter) {
     unsigned t;
     asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(counter) : "memory");
