@@ -465,9 +465,11 @@ def measure_inference(ctx, w, syn, steps, warmup, min_seconds, with_e2e, e2e_sec
         anchors_h = anchors.cpu().pin_memory()
         for i in range(3):
             pipe(anchors_h, *pin[i % 2])
+        ctx.barrier()  # probe with every rank copying at once: the ranks share the host side, and all must time the same steps
         t0 = time.perf_counter()
         pipe(anchors_h, *pin[0])
-        one = time.perf_counter() - t0
+        pipe(anchors_h, *pin[1])
+        one = ctx.vmax((time.perf_counter() - t0) / 2)
         e2e_steps = int(max(4, min(400, np.ceil(e2e_seconds / max(one, 1e-4)))))
         ctx.barrier()
         t0 = time.perf_counter()
@@ -485,7 +487,7 @@ def measure_inference(ctx, w, syn, steps, warmup, min_seconds, with_e2e, e2e_sec
         d_buf = torch.empty(h_buf.numel(), dtype=torch.float32, device=device)
         h_buf.copy_(d_buf, non_blocking=True)
         ctx.barrier()
-        n_cp = 6
+        n_cp = int(max(6, min(100, np.ceil(0.4 * e2e_steps / max(e2e_seconds, 1e-3)))))  # ~0.4 s, the same count on every rank
         t0 = time.perf_counter()
         for _ in range(n_cp):
             h_buf.copy_(d_buf, non_blocking=True)
@@ -499,7 +501,9 @@ def measure_inference(ctx, w, syn, steps, warmup, min_seconds, with_e2e, e2e_sec
                       "pcie_gbs": total_b * e2e_steps / dt / 1e9, "d2h_gbs": pipe.d2h_bytes * e2e_steps / dt / 1e9,
                       "pinned_d2h_copy_gbs": d2h_peak, "frac_of_pinned_d2h_copy": pipe.d2h_bytes * e2e_steps / dt / 1e9 / d2h_peak,
                       "limiter": "PCIe / host: the pooled features leaving the device; pinned_d2h_copy_gbs is a plain "
-                                 "cudaMemcpyAsync of the same bytes issued by all ranks at once (per-rank, slowest rank)",
+                                 "cudaMemcpyAsync of the same bytes issued by all ranks at once (per-rank, slowest rank). "
+                                 "The host side of one box moves 56 / 71 / 73 / 120 GB/s in aggregate with 1 / 2 / 4 / 8 "
+                                 "GPUs copying (profiles/r2_host_ceiling_n8.jsonl), so e2e cannot scale past ~2.1x from 1 to 8",
                       "numa": ctx.numa,
                       "how": "frcnn_pipeline_submit/_wait on pinned host buffers, two batches in flight, wall clock, max over ranks"}
         pipe.close()
