@@ -294,6 +294,18 @@ __device__ __forceinline__ void sts64(unsigned addr, u64 v) { asm volatile("st.s
 // One copy of this code serves every crop row (the hot loop should stay small: the instruction caches are 6 KB / 32 KB):
 //   g0_top  which register set holds the crop row's top feature row (the walk alternates) -- only swaps the two weights;
 //   second  second crop row of its bin-row -- flips the row bit of all codes once instead of comparing per sample.
+// acc_top += g * w_top, acc_bot += g * w_bot iff the sample's code field is clear (it holds the window maximum)
+__device__ __forceinline__ void routed_fma(unsigned field, float g, float w_top, float w_bot, float& acc_top, float& acc_bot) {
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.eq.u32 p, %2, 0;\n\t"
+        "@p fma.rn.f32 %0, %3, %4, %0;\n\t"
+        "@p fma.rn.f32 %1, %3, %5, %1;\n\t"
+        "}"
+        : "+f"(acc_top), "+f"(acc_bot)
+        : "r"(field), "f"(g), "f"(w_top), "f"(w_bot));
+}
+
 __device__ __forceinline__ void bwd_crop_row(u64 (&G0)[kS], u64 (&G1)[kS], bool g0_top, bool second, float yl, unsigned dy_addr,
                                              unsigned cw) {
     const float wt = fsub(1.0f, yl);
@@ -310,14 +322,26 @@ __device__ __forceinline__ void bwd_crop_row(u64 (&G0)[kS], u64 (&G1)[kS], bool 
         asm volatile("ld.shared.b64 %0, [%1];" : "=l"(dyv) : "r"(dy_addr + j * kPixBytes));
         const float2 d = unpack2(dyv);
         const unsigned mx = 3u << (4 * j), my = 12u << (4 * j);
+#ifdef FRCNN_AB_BWD_FSEL  // A/B: select the gradient (LOP3 + FSEL per sample and channel), packed FFMA2 on both channels
         const u64 g0 = pack2((c0 & mx) == 0u ? d.x : 0.0f, (c0 & my) == 0u ? d.y : 0.0f);
         const u64 g1 = pack2((c1 & mx) == 0u ? d.x : 0.0f, (c1 & my) == 0u ? d.y : 0.0f);
-        // (ptxas writes half of these results into the dying gradient registers and copies them back into the accumulators
-        // -- 28 moves per crop row; neither the operand order nor a tied "+l" operand changes its choice)
         G0[2 * j] = fma2(g0, w0, G0[2 * j]);
         G1[2 * j] = fma2(g0, w1, G1[2 * j]);
         G0[2 * j + 1] = fma2(g1, w0, G0[2 * j + 1]);
         G1[2 * j + 1] = fma2(g1, w1, G1[2 * j + 1]);
+#else
+        // One predicate per sample and channel guards the two scalar FMAs of that sample: 3 instructions where the select
+        // form needs LOP3 + FSEL + its share of two FFMA2 plus the copy ptxas adds to half of the packed results.
+        float2 a0 = unpack2(G0[2 * j]), b0 = unpack2(G1[2 * j]), a1 = unpack2(G0[2 * j + 1]), b1 = unpack2(G1[2 * j + 1]);
+        routed_fma(c0 & mx, d.x, w0f, w1f, a0.x, b0.x);
+        routed_fma(c0 & my, d.y, w0f, w1f, a0.y, b0.y);
+        routed_fma(c1 & mx, d.x, w0f, w1f, a1.x, b1.x);
+        routed_fma(c1 & my, d.y, w0f, w1f, a1.y, b1.y);
+        G0[2 * j] = pack2(a0.x, a0.y);
+        G1[2 * j] = pack2(b0.x, b0.y);
+        G0[2 * j + 1] = pack2(a1.x, a1.y);
+        G1[2 * j + 1] = pack2(b1.x, b1.y);
+#endif
     }
 }
 
