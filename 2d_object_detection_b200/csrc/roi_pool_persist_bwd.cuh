@@ -97,11 +97,13 @@ __global__ void __launch_bounds__(kPThreads, 1)
         const int roi_n = has_next ? idx_nxt / nch : 0, ch0_n = has_next ? (idx_nxt - roi_n * nch) * kWarpCh : 0;
         const int bin0 = roi * (kP * kP), bin0_n = roi_n * (kP * kP);
         const bool mono = (uniform(lds_u32(rec + 252)) & 0xffu) != 0u;
-        // no column inside the map, wider than the ring, or a reversed box (columns right to left): plain atomics
-        const bool slow = cls == kClsGather || box >= kBwdNumBoxes - 1 || !mono;
+        // no column inside the map or wider than the forward's ring: plain atomics.  The widest box class (27 .. 52 columns)
+        // and reversed boxes (columns right to left) keep the register sets but scatter sample by sample ("wide").
+        const bool slow = cls == kClsGather;
+        const bool wide = !slow && (box >= kBwdNumBoxes - 1 || !mono);
         const int row_bytes = (int)(uniform(lds_u32(rec + 180)) >> 16);  // tx_bytes of the record = W * 256: the forward's box
         const int W = row_bytes / kPixBytes;
-        const int nbufs = slow ? 1 : max(1, min(kBwdMaxBufs, kPBwdRowPix / max(W, 1)));
+        const int nbufs = slow ? 1 : wide ? 2 : max(1, min(kBwdMaxBufs, kPBwdRowPix / max(W, 1)));
 
         int sy = 0;
         float yl_next = lds_f32(rec + 112);
@@ -201,6 +203,49 @@ __global__ void __launch_bounds__(kPThreads, 1)
             // The walk has left feature row `kk` of the record: scatter its set along x into a zeroed row buffer and hand the
             // buffer to the TMA engine, which adds it to dFeature.
             auto flush = [&](u64(&G)[kS], int kk) {
+                if (wide) {
+                    // No carry: sample i writes its two weighted pixels into its own pair of buffer pixels and gets its own
+                    // 2-pixel reduce-add (overlapping pixels of neighbouring samples meet in L2).  The 28-pixel ring is two
+                    // halves of 7 samples, one bulk group each, so a half is rewritten while the other is still being read.
+                    float wx[16];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                     : "=f"(wx[4 * q]), "=f"(wx[4 * q + 1]), "=f"(wx[4 * q + 2]), "=f"(wx[4 * q + 3])
+                                     : "r"(rec + 16 * q));
+                    const int row = (int)lds_u16(rec + 192 + 2 * kk);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (issued >= 2) {
+                            if (lane == 0) bulk_wait_read(1);
+                            __syncwarp();
+                        }
+                        const unsigned half_off = h * (kS * kPixBytes);
+#pragma unroll
+                        for (int q = 0; q < kS / 2; ++q) {
+                            const int i = (kS / 2) * h + q;
+                            const float xl = wx[i];
+                            const float xr = fsub(okf[i], xl);
+                            sts64(lane_s + half_off + (2 * q) * kPixBytes, mul2(G[i], pack2(xr, xr)));
+                            sts64(lane_s + half_off + (2 * q + 1) * kPixBytes, mul2(G[i], pack2(xl, xl)));
+                            asm volatile("sub.rn.f32x2 %0, %0, %0;" : "+l"(G[i]));
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {
+#pragma unroll 1
+                            for (int q = 0; q < kS / 2; ++q) {
+                                const int a = (int)lds_u32(rec + 56 + 4 * ((kS / 2) * h + q));  // 0: outside, both weights 0
+                                const int xoff = a == 0 ? 0 : (a - first_off) / kPixBytes;
+                                tma_reduce_add_s2g_nocommit(&maps.dfeat[kBwdNumBoxes - 1], ch0, pix0 + row * Wf + xoff,
+                                                            warp_s + half_off + (2 * q) * kPixBytes);
+                            }
+                            bulk_commit();
+                        }
+                        ++issued;
+                    }
+                    return;
+                }
                 if (issued >= nbufs) {  // the buffer about to be reused must have been read by its reduce
                     if (lane == 0) bulk_wait_read(nbufs - 1);
                     __syncwarp();

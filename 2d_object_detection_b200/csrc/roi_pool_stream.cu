@@ -258,8 +258,9 @@ constexpr int kBwdMaxBufs = 4;
 constexpr int kBwdDySlots = 3;
 constexpr int kBwdDyBytes = kP * kPixBytes;            // 7 bins x 64 channels x 4 B
 constexpr int kBwdCodeBytes = 128;                     // 7 bins x 16 code bytes, padded
-constexpr int kBwdNumBoxes = 8;                        // row-buffer widths 6 .. 26 as in the forward (the widest class takes atomics)
-__host__ __device__ constexpr int bwd_box_width(int i) { return box_width(i); }
+constexpr int kBwdNumBoxes = 8;                        // row-buffer widths 6 .. 26 as in the forward; the last map is a 2-pixel box:
+                                                       // RoIs of the widest class (and reversed ones) reduce sample by sample
+__host__ __device__ constexpr int bwd_box_width(int i) { return i == kBwdNumBoxes - 1 ? 2 : box_width(i); }
 
 struct BwdMaps {
     CUtensorMap dfeat[kBwdNumBoxes];  // [B*Hf*Wf, C] fp32, box 64 x W: reduce-add target
@@ -274,6 +275,12 @@ __device__ __forceinline__ void tma_reduce_add_s2g(const CUtensorMap* map, int c
                  : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void tma_reduce_add_s2g_nocommit(const CUtensorMap* map, int c0, int c1, unsigned src) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map),
+                 "r"(c0), "r"(c1), "r"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read(int pending) {  // wait until at most `pending` groups still read smem
     switch (pending) {
         case 0: asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); break;
@@ -285,6 +292,11 @@ __device__ __forceinline__ void bulk_wait_read(int pending) {  // wait until at 
 __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
     u64 d;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
 __device__ __forceinline__ void sts64(unsigned addr, u64 v) { asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory"); }
