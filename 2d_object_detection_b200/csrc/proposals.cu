@@ -133,9 +133,39 @@ __device__ __forceinline__ bool tf_suppresses(const float4& a, float area_a, con
     return iou > t.thr;
 }
 
+// The same rule on SANITISED areas (sane_area: NaN stands for "area <= 0 or NaN"), the form the NMS kernel's inner loops
+// use: a degenerate box makes the union NaN, both shortcut comparisons fail, and the exact rule (on the areas recomputed
+// from the corners) decides -- three compares and two products on the common path instead of three more area tests.
+__device__ __forceinline__ float box_area(const float4& b) { return fmul(fsub(b.z, b.x), fsub(b.w, b.y)); }
+__device__ __forceinline__ float sane_area(float area) { return area > 0.0f ? area : __int_as_float(0x7fc00000); }
+__device__ __forceinline__ bool tf_suppresses_sane(const float4& a, float sa, const float4& b, float sb, const NmsThreshold& t) {
+    const float d0 = fmaxf(fsub(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.0f);
+    const float d1 = fmaxf(fsub(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.0f);
+    const float inter = fmul(d0, d1);
+    const float uni = fsub(fadd(sa, sb), inter);
+    const bool normal = uni >= 1.0e-30f;  // (false for NaN: a degenerate box)
+    // the common outcome first (most pairs do not overlap at all); `&`: one combined predicate, one branch
+    if (normal & (inter < fmul(t.lo, uni))) return false;
+    if (normal & (inter > fmul(t.hi, uni))) return true;
+    return tf_suppresses(a, box_area(a), b, box_area(b), t);
+}
+
 __device__ __forceinline__ uint64_t composite(uint32_t key, uint32_t idx) {
     return (static_cast<uint64_t>(key) << 32) | static_cast<uint64_t>(0xffffffffu - idx);
 }
+
+// Outputs of postprocess_output for a single-class call (the RPN form): with one class per image there is nothing to merge,
+// so the NMS CTA of an image writes the padded outputs itself and the finalize launch disappears (out_boxes == nullptr:
+// not fused -- the multi-class form, or the stand-alone NMS entry point).
+struct NmsFinalize {
+    float4* out_boxes;
+    float* out_scores;
+    int32_t* out_classes;
+    int32_t* out_valid;
+    int32_t* out_idx;
+    int32_t* out_exhausted;
+    int R;
+};
 
 struct NmsShared {
     unsigned long long hi;        // exclusive upper bound of unvisited composites
@@ -144,11 +174,80 @@ struct NmsShared {
     int need, want_max, want_min, expect, kept, budget, remaining, stop, select_done;
     unsigned int cnt;
     unsigned int wsum[32], wtotal; // block-wide scan of the histogram: candidates in the warps before a warp, all candidates
-    unsigned int dead[2];         // per 64-block: candidates suppressed by already kept boxes
-    unsigned int diag[128];       // per 64-block: 64x64 suppression bits among the block (row r: words 2r, 2r+1)
+    unsigned int wmax[32], wmin[32]; // per-warp largest / smallest candidate key (keys in shared memory)
+    // per 64-block, double-buffered by block parity (the buffer of the next block is zeroed while this block is resolved):
+    unsigned int dead[2][2];      // candidates suppressed by already kept boxes
+    unsigned int diag[2][128];    // 64x64 suppression bits among the block (row r: words 2r, 2r+1)
 };
 
 constexpr size_t kNmsSharedBytes = (sizeof(NmsShared) + 15) / 16 * 16;
+
+// One row of the padded outputs (post_processing.py:57-63): the kept box clipped to [0,1] (clip_boxes=True), its score and
+// class; zeros (and index -1) past the valid detections.
+__device__ __forceinline__ void write_detection(float4* __restrict__ out_boxes, float* __restrict__ out_scores,
+                                                int32_t* __restrict__ out_classes, int32_t* __restrict__ out_idx, size_t row,
+                                                bool valid, const float4* __restrict__ seg_boxes,
+                                                const uint32_t* __restrict__ seg_keys, int idx, int cls) {
+    float4 ob = make_float4(0.f, 0.f, 0.f, 0.f);
+    float os = 0.f;
+    int oc = 0, oi = -1;
+    if (valid) {
+        const float4 v = seg_boxes[idx];
+        ob = make_float4(fmaxf(fminf(v.x, 1.f), 0.f), fmaxf(fminf(v.y, 1.f), 0.f), fmaxf(fminf(v.z, 1.f), 0.f),
+                         fmaxf(fminf(v.w, 1.f), 0.f));
+        os = key_score(seg_keys[idx]);
+        oc = cls;
+        oi = idx;
+    }
+    out_boxes[row] = ob;
+    out_scores[row] = os;
+    out_classes[row] = oc;
+    if (out_idx) out_idx[row] = oi;
+}
+
+__device__ __forceinline__ uint4 lds_u4(const uint32_t* p) {
+    uint4 q;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
+                 : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return q;
+}
+__device__ __forceinline__ uint32_t lds_u1(const uint32_t* p) {
+    uint32_t q;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(q) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return q;
+}
+
+// One sweep over the N score keys of a segment: f(key, index) for every key.  kShared: the keys sit in shared memory (copied
+// there once per launch when they fit); otherwise they are read from global memory.  128-bit loads, four of them in flight
+// per thread before the first key is consumed (the sweeps are latency chains otherwise: ~4 dependent round trips per thread
+// at N = 16848).
+template <bool kShared, class F>
+__device__ __forceinline__ void for_each_key(const uint32_t* __restrict__ base, bool vec4, int N, int tid, F&& f) {
+    if (vec4) {
+        const int n4 = N >> 2;
+        auto load4 = [&](int v) { return kShared ? lds_u4(base + 4 * v) : __ldg(reinterpret_cast<const uint4*>(base) + v); };
+        auto use4 = [&](const uint4& q, int v) {
+            f(q.x, 4 * v);
+            f(q.y, 4 * v + 1);
+            f(q.z, 4 * v + 2);
+            f(q.w, 4 * v + 3);
+        };
+        int v = tid;
+        if (!kShared)  // (shared memory: the plain loop below -- short latency, and the unrolled body is a lot of cold code)
+        for (; v + 3 * kNmsThreads < n4; v += 4 * kNmsThreads) {  // whole groups: four unconditional loads, then the work
+            const uint4 q0 = load4(v), q1 = load4(v + kNmsThreads), q2 = load4(v + 2 * kNmsThreads), q3 = load4(v + 3 * kNmsThreads);
+            use4(q0, v);
+            use4(q1, v + kNmsThreads);
+            use4(q2, v + 2 * kNmsThreads);
+            use4(q3, v + 3 * kNmsThreads);
+        }
+        for (; v < n4; v += kNmsThreads) use4(load4(v), v);
+        for (int n = (n4 << 2) + tid; n < N; n += kNmsThreads) f(kShared ? lds_u1(base + n) : __ldg(base + n), n);
+    } else {
+        for (int n = tid; n < N; n += kNmsThreads) f(kShared ? lds_u1(base + n) : __ldg(base + n), n);
+    }
+}
 
 // One persistent CTA per (image, class) segment.
 //   loop over REFILLS of the candidate list in (score desc, index asc) order:
@@ -162,10 +261,12 @@ constexpr size_t kNmsSharedBytes = (sizeof(NmsShared) + 15) / 16 * 16;
 //              broadcast reads), (b) all threads build the 64x64 bitmask of the block, (c) one warp resolves the
 //              block with register bit operations and appends the survivors to the kept list.
 //   The loop ends as soon as `cap` boxes are kept -- TF's greedy loop exactly, no pre-NMS cut needed (trap T1).
+// keys_in_smem: the segment's N score keys are copied to shared memory once and every later sweep (two or three histogram
+// sweeps + one collect sweep per refill) reads them there (N <= ~40k: the KITTI grids); larger segments sweep global memory.
 __global__ void __launch_bounds__(kNmsThreads, 1)
     nms_select_kernel(const float4* __restrict__ boxes, const uint32_t* __restrict__ keys, int N, int cap, int top_n,
                       float iou_thr, int32_t* __restrict__ kept_idx, int32_t* __restrict__ kept_count,
-                      int32_t* __restrict__ exhausted) {
+                      int32_t* __restrict__ exhausted, int keys_in_smem, const NmsFinalize fin) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // 8-byte items first, then 16-byte boxes, then 4-byte arrays: every sub-array stays naturally aligned for any cap
     NmsShared* S = reinterpret_cast<NmsShared*>(smem_raw);
@@ -175,6 +276,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
     float* carea = reinterpret_cast<float*>(kbox + cap);                                    // [kChunk]
     float* karea = carea + kChunk;                                                         // [cap]
     unsigned int* hist = reinterpret_cast<unsigned int*>(karea + cap);                      // [kBins]
+    uint32_t* skey_s = reinterpret_cast<uint32_t*>(                                         // [N] (keys_in_smem), 16-byte aligned
+        (reinterpret_cast<uintptr_t>(hist + kBins) + 15) & ~static_cast<uintptr_t>(15));
 
     const int seg = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -190,9 +293,87 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
         S->stop = 0;
     }
     int flag_exhausted = 0;
-    __syncthreads();
+    const bool vec4 = (reinterpret_cast<uintptr_t>(skeys) & 15u) == 0;  // this segment's keys allow 128-bit loads
+    // Keys are selected RELATIVE TO THE LARGEST candidate key: adding koff moves it to 0xfffffffe (a translation: the
+    // order, and so every selected set, is unchanged; not 0xffffffff, so that every composite stays below the initial
+    // bound hi = ~0), and the leading `lead` bits that the largest and the smallest candidate then share are known.  The
+    // radix passes start below them.  Scores are probabilities: half of them lie
+    // in [0.5, 1), which is FOUR bins of a histogram over the top 11 bits of the raw float key -- thousands of same-address
+    // shared-memory atomics per sweep; below the common leading bits the same keys spread over 64 bins or more.
+    uint32_t koff = 0u;
+    uint32_t cand_lo = 1u;                          // no candidate's translated key lies below this (a key 0 is no candidate)
+    unsigned long long pfx0 = 0ull, pmask0 = 0ull;  // the decided leading bits of every candidate's composite
+    if (keys_in_smem) {
+        uint32_t kmax = 0u, kmin = 0xffffffffu;
+        auto seen = [&](uint32_t k) {
+            if (k != 0u) {
+                kmax = max(kmax, k);
+                kmin = min(kmin, k);
+            }
+        };
+        auto seen4 = [&](const uint4& q) {
+            seen(q.x);
+            seen(q.y);
+            seen(q.z);
+            seen(q.w);
+        };
+        if (vec4) {
+            const int n4 = N >> 2;
+            const uint4* k4 = reinterpret_cast<const uint4*>(skeys);
+            uint4* s4 = reinterpret_cast<uint4*>(skey_s);
+            int v = tid;
+            for (; v + 3 * kNmsThreads < n4; v += 4 * kNmsThreads) {
+                const uint4 q0 = __ldg(k4 + v), q1 = __ldg(k4 + v + kNmsThreads), q2 = __ldg(k4 + v + 2 * kNmsThreads),
+                            q3 = __ldg(k4 + v + 3 * kNmsThreads);
+                s4[v] = q0;
+                s4[v + kNmsThreads] = q1;
+                s4[v + 2 * kNmsThreads] = q2;
+                s4[v + 3 * kNmsThreads] = q3;
+                seen4(q0);
+                seen4(q1);
+                seen4(q2);
+                seen4(q3);
+            }
+            for (; v < n4; v += kNmsThreads) {
+                const uint4 q = __ldg(k4 + v);
+                s4[v] = q;
+                seen4(q);
+            }
+            for (int n = (n4 << 2) + tid; n < N; n += kNmsThreads) {
+                const uint32_t k = __ldg(skeys + n);
+                skey_s[n] = k;
+                seen(k);
+            }
+        } else {
+            for (int n = tid; n < N; n += kNmsThreads) {
+                const uint32_t k = __ldg(skeys + n);
+                skey_s[n] = k;
+                seen(k);
+            }
+        }
+        kmax = __reduce_max_sync(0xffffffffu, kmax);
+        kmin = __reduce_min_sync(0xffffffffu, kmin);
+        if (lane == 0) {
+            S->wmax[warp] = kmax;
+            S->wmin[warp] = kmin;
+        }
+        __syncthreads();
+        kmax = __reduce_max_sync(0xffffffffu, S->wmax[lane]);
+        kmin = __reduce_min_sync(0xffffffffu, S->wmin[lane]);
+        if (kmax != 0u) {  // (no candidate at all: the first histogram is empty and the loop ends)
+            koff = 0xfffffffeu - kmax;
+            cand_lo = kmin + koff;
+            const uint32_t x = 0xfffffffeu ^ (kmin + koff);  // translated extremes: everything between shares their prefix
+            const int lead = x ? __clz((int)x) : 32;
+            // undecided composite bits: [0, 64 - lead); all keys equal leaves the index half (bits 22..31 of ~idx are ones)
+            pmask0 = lead == 0 ? 0ull : lead == 32 ? 0xffffffffffc00000ull : (~0ull << (64 - lead));
+            pfx0 = 0xfffffffeffffffffull & pmask0;
+        }
+    } else {
+        __syncthreads();
+    }
 #ifdef FRCNN_NMS_TIMING  // debug build: time spent per phase (block 0, thread 0; printed at the end)
-    long long t_mark = clock64(), t_phase[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long t_mark = clock64(), t_phase[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     int n_chunks = 0, n_blocks = 0;
 #define NMS_TICK(i)                                   \
     do {                                              \
@@ -205,13 +386,12 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
 #endif
 
     const NmsThreshold nthr = NmsThreshold::make(iou_thr);
-    const bool vec4 = (reinterpret_cast<uintptr_t>(skeys) & 15u) == 0;  // this segment's keys allow 128-bit loads
 
     while (true) {
         // ===================== SELECT ===================================================================
         if (tid == 0) {
-            S->pfx = 0;
-            S->pmask = 0;
+            S->pfx = pfx0;
+            S->pmask = pmask0;
             const int budget = S->budget;
             // list target per refill.  The greedy loop usually reaches `cap` long before pre_nms_top_n candidates have been
             // visited (KITTI: 300 kept after ~700 of 2000), so short lists that are selected lazily beat one exact select of
@@ -228,35 +408,51 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
         }
         __syncthreads();
         const unsigned long long hi = S->hi;
-        for (int pass = 0; pass < 5; ++pass) {
-            // digit layout: key bits 31..21, 20..10, 9..0 ; then ~idx bits 21..11, 10..0 (idx < 2^22)
-            const int shift = pass == 0 ? 53 : pass == 1 ? 42 : pass == 2 ? 32 : pass == 3 ? 11 : 0;
-            const int nb = pass == 2 ? 1024 : kBins;
+        for (int pass = 0;; ++pass) {
+            const unsigned long long pfx = S->pfx, pmask = S->pmask;  // (written before the barrier that ended the last pass)
+            // digit layout: 11 bits at a time from the highest undecided bit of the (translated) key down to its bit 0 (the
+            // last key digit takes what is left), then ~idx bits 21..11 and 10..0 (idx < 2^22).  pmask is a run of leading
+            // ones, so the highest undecided bit is 63 - clz(~pmask).
+            const int top = 64 - __clzll((long long)~pmask);
+            const int width = top > 32 ? min(11, top - 32) : 11;
+            const int shift = top - width;
+            const int nb = 1 << width;
             for (int i = tid; i < nb; i += kNmsThreads) hist[i] = 0;
             __syncthreads();
-            const unsigned long long pfx = S->pfx, pmask = S->pmask;
+            NMS_TICK(14);
             // one histogram sweep over the keys: 128-bit loads (four keys per thread and iteration, independent of each
             // other, so the loads of a thread overlap) and one fire-and-forget shared-memory atomic per participating key --
             // the match_any aggregation it replaces cost more than the bank conflicts it avoided (4.7 us per sweep; eight
             // private copies of the histogram were tried too: zeroing and summing them costs more than the conflicts)
             auto count_key = [&](uint32_t k, int n) {
-                const unsigned long long c = composite(k, (uint32_t)n);
+                const unsigned long long c = composite(k + koff, (uint32_t)n);
                 if ((k != 0u) && (c < hi) && ((c & pmask) == pfx))
                     atomicAdd(&hist[(unsigned int)(c >> shift) & (unsigned int)(nb - 1)], 1u);
             };
-            if (vec4) {
-                const uint4* k4 = reinterpret_cast<const uint4*>(skeys);
-                for (int v = tid; v < N / 4; v += kNmsThreads) {
-                    const uint4 q = k4[v];
-                    count_key(q.x, 4 * v);
-                    count_key(q.y, 4 * v + 1);
-                    count_key(q.z, 4 * v + 2);
-                    count_key(q.w, 4 * v + 3);
+            // While the digit lies in the key half (nearly always the only passes), everything is decided on 32 bits: the
+            // keys that carry the current prefix and lie below the bound form ONE interval [lo_r, lo_r + span], so a key
+            // takes a subtraction and an unsigned compare (a key that is not a candidate, 0, lands below every candidate's
+            // translated key); only a key equal to the bound's key half looks at its index.
+            const unsigned int pm_k = (unsigned int)(pmask >> 32), pf_k = (unsigned int)(pfx >> 32);
+            const unsigned int hi_k = (unsigned int)(hi >> 32), hi_i = (unsigned int)hi;
+            const unsigned int lo_r = max(pf_k, cand_lo), hi_r = min(pf_k | ~pm_k, hi_k);
+            const unsigned int span = hi_r - lo_r;
+            const int sh_k = shift - 32;
+            auto count_key32 = [&](uint32_t k, int n) {
+                const unsigned int kk = k + koff;
+                if (kk - lo_r <= span && (kk != hi_k || (0xffffffffu - (unsigned int)n) < hi_i))
+                    atomicAdd(&hist[(kk >> sh_k) & (unsigned int)(nb - 1)], 1u);
+            };
+            if (shift >= 32) {
+                if (hi_r >= lo_r) {
+                    if (keys_in_smem) for_each_key<true>(skey_s, true, N, tid, count_key32);
+                    else for_each_key<false>(skeys, vec4, N, tid, count_key32);
                 }
-                for (int n = (N / 4) * 4 + tid; n < N; n += kNmsThreads) count_key(skeys[n], n);
             } else {
-                for (int n = tid; n < N; n += kNmsThreads) count_key(skeys[n], n);
+                if (keys_in_smem) for_each_key<true>(skey_s, true, N, tid, count_key);
+                else for_each_key<false>(skeys, vec4, N, tid, count_key);
             }
+            NMS_TICK(15);
             __syncthreads();
             {   // Block-wide scan of the histogram in descending digit order (position p <-> digit nb - 1 - p): every thread
                 // sums its K digits, warp scans + one scan of the 32 warp totals give each thread the number of candidates
@@ -264,10 +460,12 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
                 // digits per lane did this before: as long as a sweep over the keys.)
                 int need = S->need;            // still wanted from inside the current prefix (read before anybody writes)
                 const int got = S->expect;     // already secured by bins above the current prefix
-                const int K = nb / kNmsThreads;  // 2 (11-bit digits) or 1 (10-bit digit of pass 2)
-                const int top_bin = nb - 1 - tid * K;
+                const int K = nb > kNmsThreads ? nb / kNmsThreads : 1;  // 2 (11-bit digits) or 1 (narrower last key digit)
+                const int top_bin = nb - 1 - tid * K;                   // (negative: a thread beyond a narrow digit's bins)
                 unsigned int hk[2] = {0u, 0u};  // this thread's digits
-                for (int q = 0; q < K; ++q) hk[q] = hist[top_bin - q];
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+                    if (q < K && top_bin - q >= 0) hk[q] = hist[top_bin - q];
                 const unsigned int sum = hk[0] + hk[1];
                 unsigned int incl = sum;
                 for (int o = 1; o < 32; o <<= 1) {
@@ -295,9 +493,10 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
                 }
                 if (need > 0 && excl < (unsigned)need && (unsigned)need <= excl + sum) {  // exactly one thread
                     unsigned int cum = excl;
-                    for (int q = 0; q < K; ++q) {
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
                         const unsigned int h = hk[q];
-                        if (cum + h >= (unsigned)need) {
+                        if (q < K && cum + h >= (unsigned)need) {
                             const unsigned long long bin = (unsigned long long)(top_bin - q);
                             unsigned long long npfx = pfx | (bin << shift);
                             unsigned long long nmask = pmask | ((unsigned long long)(nb - 1) << shift);
@@ -311,7 +510,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
                                 S->expect = got + (int)cum;
                                 S->select_done = 1;
                             } else {
-                                if (pass == 2) {  // bits 22..31 of ~idx are constant ones
+                                if (shift == 32) {  // the key is decided; bits 22..31 of ~idx are constant ones
                                     npfx |= 0xffc00000ull;
                                     nmask |= 0xffc00000ull;
                                 }
@@ -332,6 +531,9 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
         }
         const int expect = S->expect;
         NMS_TICK(0);
+#ifdef FRCNN_NMS_TIMING
+        ++n_chunks;
+#endif
         if (expect == 0) break;  // no candidates left (uniform)
         const unsigned long long thresh = S->thresh;
 
@@ -339,27 +541,93 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
         // Only ~ one key in 30 is taken, so every taker simply reserves its slot with a shared-memory atomic (the order
         // inside the list is irrelevant: it is sorted next); 128-bit key loads as in the histogram sweeps.
         auto collect_key = [&](uint32_t k, int n) {
-            const unsigned long long c = composite(k, (uint32_t)n);
+            const unsigned long long c = composite(k + koff, (uint32_t)n);
             if ((k != 0u) && (c < hi) && (c >= thresh)) {
                 const unsigned int pos = atomicAdd(&S->cnt, 1u);
                 if (pos < (unsigned)kList) comp[pos] = c;
             }
         };
-        if (vec4) {
-            const uint4* k4 = reinterpret_cast<const uint4*>(skeys);
-            for (int v = tid; v < N / 4; v += kNmsThreads) {
-                const uint4 q = k4[v];
-                collect_key(q.x, 4 * v);
-                collect_key(q.y, 4 * v + 1);
-                collect_key(q.z, 4 * v + 2);
-                collect_key(q.w, 4 * v + 3);
+        if (keys_in_smem) {
+            // Keys in shared memory: no atomics at all.  Sweep 1: every thread marks its takers in a 64-bit mask (bit 4 r + e
+            // = key e of the thread's r-th 128-bit load; bit 63 = its key of the unaligned tail).  A block-wide exclusive
+            // scan of the counts gives each thread its first slot (every warp scans the 32 warp totals itself: one barrier).
+            // Sweep 2: the few threads that own a taker reload that load and write.  (One shared-memory atomic per taker on
+            // the list counter, all 32 warps on one address, cost 5.6 k cycles per refill; this costs about 2 k.)
+            const int n4 = N >> 2;
+            const unsigned int hi_k = (unsigned int)(hi >> 32), th_k = (unsigned int)(thresh >> 32);
+            // key half first: one subtraction + unsigned compare against [max(th_k, cand_lo), hi_k] (a key 0, not a
+            // candidate, lands below cand_lo); only keys that tie with a bound compare whole composites
+            const unsigned int lo_c = max(th_k, cand_lo), span_c = hi_k - lo_c;  // (hi_k >= th_k >= ... : thresh < hi)
+            const bool th_tie = (unsigned int)thresh != 0u;
+            auto takes = [&](uint32_t k, int n) {
+                const unsigned int kk = k + koff;
+                bool take = kk - lo_c <= span_c;
+                if (take && (kk == hi_k || (th_tie && kk == th_k))) {
+                    const unsigned long long c = composite(kk, (uint32_t)n);
+                    take = c < hi && c >= thresh;
+                }
+                return take;
+            };
+            unsigned long long mask = 0ull;
+            {
+                int r = 0;
+                for (int v = tid; v < n4; v += kNmsThreads, ++r) {
+                    const uint4 q = lds_u4(skey_s + 4 * v);
+                    const unsigned int nib = (takes(q.x, 4 * v) ? 1u : 0u) | (takes(q.y, 4 * v + 1) ? 2u : 0u) |
+                                             (takes(q.z, 4 * v + 2) ? 4u : 0u) | (takes(q.w, 4 * v + 3) ? 8u : 0u);
+                    mask |= (unsigned long long)nib << (4 * r);
+                }
+                const int n = (n4 << 2) + tid;
+                if (n < N && takes(lds_u1(skey_s + n), n)) mask |= 1ull << 63;
             }
-            for (int n = (N / 4) * 4 + tid; n < N; n += kNmsThreads) collect_key(skeys[n], n);
+            NMS_TICK(9);
+            const int mine = __popcll(mask);
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) S->wsum[warp] = (unsigned int)incl;
+            __syncthreads();
+            int wincl = (int)S->wsum[lane];
+            NMS_TICK(10);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, wincl, o);
+                if (lane >= o) wincl += t;
+            }
+            const int wbase = warp == 0 ? 0 : __shfl_sync(0xffffffffu, wincl, (warp + 31) & 31);
+            if (tid == kNmsThreads - 1) S->cnt = (unsigned int)wincl;  // (lane 31: the block total)
+            NMS_TICK(11);
+            if (mask) {
+                unsigned int pos = (unsigned int)(wbase + incl - mine);
+                int r = 0;
+                for (int v = tid; v < n4; v += kNmsThreads, ++r) {
+                    const unsigned int nib = (unsigned int)(mask >> (4 * r)) & 15u;
+                    if (nib == 0u) continue;
+                    const uint4 q = lds_u4(skey_s + 4 * v);
+                    const unsigned int kq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if ((nib >> e) & 1u) {
+                            if (pos < (unsigned)kList) comp[pos] = composite(kq[e] + koff, (uint32_t)(4 * v + e));
+                            ++pos;
+                        }
+                    }
+                }
+                if (mask >> 63) {
+                    const int n = (n4 << 2) + tid;
+                    if (pos < (unsigned)kList) comp[pos] = composite(lds_u1(skey_s + n) + koff, (uint32_t)n);
+                }
+            }
+            NMS_TICK(12);
         } else {
-            for (int n = tid; n < N; n += kNmsThreads) collect_key(skeys[n], n);
+            for_each_key<false>(skeys, vec4, N, tid, collect_key);
         }
         __syncthreads();
         const int m = min((int)S->cnt, kList);  // == expect by construction
+        NMS_TICK(13);
         int p2 = 32;
         while (p2 < m) p2 <<= 1;
         for (int i = m + tid; i < p2; i += kNmsThreads) comp[i] = 0ull;
@@ -408,8 +676,10 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
             const float4 b = __ldg(sboxes + idx);
             const float4 nb4 = make_float4(fminf(b.x, b.z), fminf(b.y, b.w), fmaxf(b.x, b.z), fmaxf(b.y, b.w));
             cbox[tid] = nb4;
-            carea[tid] = fmul(fsub(nb4.z, nb4.x), fsub(nb4.w, nb4.y));
+            carea[tid] = sane_area(box_area(nb4));  // (carea / karea hold sanitised areas: tf_suppresses_sane)
         }
+        if (tid < 128) S->diag[0][tid] = 0u;  // bitmask buffers of the first 64-block (block b uses buffer b & 1)
+        if (tid < 2) S->dead[0][tid] = 0u;
         __syncthreads();
 
         NMS_TICK(3);
@@ -420,23 +690,30 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
             if (kept >= cap) break;
             const int base = blk * 64;
             const int nvalid = min(64, ms - base);
-            if (tid < 128) S->diag[tid] = 0u;
-            if (tid < 2) S->dead[tid] = 0u;
-            __syncthreads();
+            unsigned int* const diag = S->diag[blk & 1];
+            unsigned int* const dead = S->dead[blk & 1];
             NMS_TICK(5);
+#ifdef FRCNN_NMS_TIMING
+            ++n_blocks;
+#endif
             {   // (a) block vs kept list: thread = (candidate, one of 16 interleaved slices of the kept list)
                 const int cand = tid & 63, part = tid >> 6;
                 if (cand < nvalid && part < kept) {
                     const float4 bt = cbox[base + cand];
                     const float at = carea[base + cand];
                     bool sup = false;
-                    for (int j = part; j < kept; j += kNmsThreads / 64) {
-                        if (tf_suppresses(bt, at, kbox[j], karea[j], nthr)) {
-                            sup = true;
-                            break;
-                        }
+                    // this thread's slice of the kept list: boxes part, part + 16, ... ; four per round at immediate offsets
+                    constexpr int kStep = kNmsThreads / 64;
+                    const float4* kb = kbox + part;
+                    const float* ka = karea + part;
+                    int left = (kept - part + kStep - 1) / kStep;
+                    for (; left >= 4 && !sup; left -= 4, kb += 4 * kStep, ka += 4 * kStep) {
+                        sup = tf_suppresses_sane(bt, at, kb[0], ka[0], nthr) || tf_suppresses_sane(bt, at, kb[kStep], ka[kStep], nthr) ||
+                              tf_suppresses_sane(bt, at, kb[2 * kStep], ka[2 * kStep], nthr) ||
+                              tf_suppresses_sane(bt, at, kb[3 * kStep], ka[3 * kStep], nthr);
                     }
-                    if (sup) atomicOr(&S->dead[cand >> 5], 1u << (cand & 31));
+                    for (; left > 0 && !sup; --left, kb += kStep, ka += kStep) sup = tf_suppresses_sane(bt, at, kb[0], ka[0], nthr);
+                    if (sup) atomicOr(&dead[cand >> 5], 1u << (cand & 31));
                 }
             }
             {   // (b) 64x64 upper triangle of the block: thread = (row, group of 4 columns)
@@ -448,41 +725,40 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const int u = 4 * g + q;
-                        if (u > row && u < nvalid && tf_suppresses(bt, at, cbox[base + u], carea[base + u], nthr))
+                        if (u > row && u < nvalid && tf_suppresses_sane(bt, at, cbox[base + u], carea[base + u], nthr))
                             bits |= 1u << q;
                     }
-                    if (bits) atomicOr(&S->diag[2 * row + (g >> 3)], bits << ((4 * g) & 31));
+                    if (bits) atomicOr(&diag[2 * row + (g >> 3)], bits << ((4 * g) & 31));
                 }
             }
             NMS_TICK(6);
             __syncthreads();
             NMS_TICK(7);
             if (warp == 0) {  // (c) resolve: lane l holds the mask rows l and l+32, as 32-bit words (row r only has bits > r)
-                const unsigned long long valid = nvalid == 64 ? ~0ull : ((1ull << nvalid) - 1ull);
-                unsigned int cur_lo = S->dead[0] | ~(unsigned int)valid, cur_hi = S->dead[1] | ~(unsigned int)(valid >> 32);
-                const unsigned int r0_lo = S->diag[2 * lane], r0_hi = S->diag[2 * lane + 1], r1_hi = S->diag[2 * (lane + 32) + 1];
-                unsigned int keep_lo = 0u, keep_hi = 0u;
-                int room = cap - kept;
+                const unsigned int vlo = nvalid >= 32 ? ~0u : ((1u << nvalid) - 1u);
+                const unsigned int vhi = nvalid == 64 ? ~0u : nvalid > 32 ? ((1u << (nvalid - 32)) - 1u) : 0u;
+                // cur: suppressed (or beyond the block).  Row i only sets bits above i, so bit i is final when step i reads it
+                // and the survivors are simply the bits still clear at the end: one test and two guarded ORs per step.
+                unsigned int cur_lo = dead[0] | ~vlo, cur_hi = dead[1] | ~vhi;
+                const unsigned int r0_lo = diag[2 * lane], r0_hi = diag[2 * lane + 1], r1_hi = diag[2 * (lane + 32) + 1];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const unsigned int lo = __shfl_sync(0xffffffffu, r0_lo, i), hi = __shfl_sync(0xffffffffu, r0_hi, i);
-                    if (!(cur_lo & (1u << i)) && room > 0) {
-                        keep_lo |= 1u << i;
+                    if (!(cur_lo & (1u << i))) {
                         cur_lo |= lo;
                         cur_hi |= hi;
-                        --room;
                     }
                 }
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const unsigned int hi = __shfl_sync(0xffffffffu, r1_hi, i);
-                    if (!(cur_hi & (1u << i)) && room > 0) {
-                        keep_hi |= 1u << i;
-                        cur_hi |= hi;
-                        --room;
-                    }
+                    if (!(cur_hi & (1u << i))) cur_hi |= hi;
                 }
-                const unsigned long long keepbits = (unsigned long long)keep_lo | ((unsigned long long)keep_hi << 32);
+                unsigned long long keepbits = ~((unsigned long long)cur_lo | ((unsigned long long)cur_hi << 32));
+                // the cap ends the greedy loop: only the first cap - kept survivors count (earlier decisions do not depend on
+                // later candidates, so cutting the tail afterwards is the same loop)
+                const int room = cap - kept;
+                while (__popcll(keepbits) > room) keepbits &= ~(1ull << (63 - __clzll(keepbits)));
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {  // append survivors (lane handles bits lane and lane+32)
                     const int i = lane + 32 * h;
@@ -494,6 +770,9 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
                     }
                 }
                 if (lane == 0) S->kept = kept + __popcll(keepbits);
+            } else if (warp <= 4) {  // meanwhile: zero the bitmask buffers of the next block
+                S->diag[(blk + 1) & 1][tid - 32] = 0u;
+                if (tid < 34) S->dead[(blk + 1) & 1][tid - 32] = 0u;
             }
             __syncthreads();
             NMS_TICK(8);
@@ -521,15 +800,25 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
     __syncthreads();
     const int kept = S->kept;
 #ifdef FRCNN_NMS_TIMING
-    if (tid == 0 && blockIdx.x == 0)
-        printf("nms timing (cycles): select %lld collect %lld sort %lld load %lld greedy-rest %lld | per block: zero+bar %lld  a+b(thread 0) %lld  "
-               "bar %lld  resolve+bar %lld   kept %d\n", t_phase[0], t_phase[1], t_phase[2], t_phase[3], t_phase[4], t_phase[5], t_phase[6],
-               t_phase[7], t_phase[8], kept);
+    if (tid == 0)
+        printf("nms timing block %d refills %d blocks %d (cycles): select %lld collect %lld sort %lld load %lld greedy-rest %lld | per block: zero+bar %lld  a+b(thread 0) %lld  "
+               "bar %lld  resolve+bar %lld   kept %d | collect: sweep1 %lld bar %lld scan %lld sweep2 %lld bar %lld pad %lld | select: zero+bar %lld sweep %lld scan+bar %lld\n", (int)blockIdx.x, n_chunks, n_blocks, t_phase[0], t_phase[1], t_phase[2], t_phase[3], t_phase[4], t_phase[5], t_phase[6],
+               t_phase[7], t_phase[8], kept, t_phase[9], t_phase[10], t_phase[11], t_phase[12], t_phase[13], t_phase[1], t_phase[14], t_phase[15], t_phase[0]);
 #endif
     for (int i = kept + tid; i < cap; i += kNmsThreads) sidx[i] = -1;
     if (tid == 0) {
         kept_count[seg] = kept;
         if (exhausted) exhausted[seg] = flag_exhausted;
+    }
+    if (fin.out_boxes) {  // single class: this segment is image `seg`; the kept list is already in score order
+        const int nv = min(kept, fin.R);
+        for (int t = tid; t < fin.R; t += kNmsThreads)
+            write_detection(fin.out_boxes, fin.out_scores, fin.out_classes, fin.out_idx, (size_t)seg * fin.R + t, t < nv, sboxes, skeys,
+                            t < nv ? sidx[t] : -1, 0);  // (sidx: written by this CTA before the barrier above)
+        if (tid == 0) {
+            fin.out_valid[seg] = nv;
+            if (fin.out_exhausted) fin.out_exhausted[seg] = flag_exhausted;
+        }
     }
 }
 
@@ -581,28 +870,15 @@ __global__ void __launch_bounds__(1024)
             }
     }
     for (int t = tid; t < R; t += blockDim.x) {
-        float4 ob = make_float4(0.f, 0.f, 0.f, 0.f);
-        float os = 0.f;
-        int oc = 0, oi = -1;
-        if (t < nv) {
-            int c = 0, rank = t;
-            if (nc > 1) {
-                const uint32_t ord = 0xffffffffu - (uint32_t)(comp[t] & 0xffffffffull);
-                c = (int)(ord / (uint32_t)cap);
-                rank = (int)(ord % (uint32_t)cap);
-            }
-            const size_t seg = (size_t)b * nc + c;
-            oi = kept_idx[seg * cap + rank];
-            const float4 v = boxes_rel[seg * N + oi];
-            ob = make_float4(fmaxf(fminf(v.x, 1.f), 0.f), fmaxf(fminf(v.y, 1.f), 0.f), fmaxf(fminf(v.z, 1.f), 0.f),
-                             fmaxf(fminf(v.w, 1.f), 0.f));  // clip_boxes=True
-            os = key_score(keys[seg * N + oi]);
-            oc = c;
+        int c = 0, rank = t;
+        if (t < nv && nc > 1) {
+            const uint32_t ord = 0xffffffffu - (uint32_t)(comp[t] & 0xffffffffull);
+            c = (int)(ord / (uint32_t)cap);
+            rank = (int)(ord % (uint32_t)cap);
         }
-        out_boxes[(size_t)b * R + t] = ob;
-        out_scores[(size_t)b * R + t] = os;
-        out_classes[(size_t)b * R + t] = oc;
-        if (out_idx) out_idx[(size_t)b * R + t] = oi;
+        const size_t seg = (size_t)b * nc + c;
+        write_detection(out_boxes, out_scores, out_classes, out_idx, (size_t)b * R + t, t < nv, boxes_rel + seg * N, keys + seg * N,
+                        t < nv ? kept_idx[seg * cap + rank] : -1, c);
     }
     if (tid == 0) {
         out_valid[b] = nv;
@@ -642,13 +918,18 @@ static PostWs carve_post_ws(void* base, int B, int N, int nc, int cap) {
 }
 
 static int launch_nms(const float4* boxes, const uint32_t* keys, int segments, int N, int cap, int top_n, float iou_thr,
-                      int32_t* kept_idx, int32_t* kept_count, int32_t* exhausted, cudaStream_t st) {
+                      int32_t* kept_idx, int32_t* kept_count, int32_t* exhausted, cudaStream_t st,
+                      const NmsFinalize& fin = NmsFinalize{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0}) {
     FRCNN_REQUIRE(cap <= 4096, FRCNN_ELIMIT, "nms: min(max_output, N) = %d exceeds the 4096 limit", cap);
     FRCNN_REQUIRE(N < (1 << 22), FRCNN_ELIMIT, "nms: N = %d exceeds the 2^22 limit", N);
-    const size_t smem = nms_smem_bytes(cap);
+    size_t smem = nms_smem_bytes(cap);
+    // the segment's keys stay in shared memory across the sweeps when they fit beside the lists (227 KB per CTA on sm_100)
+    const size_t with_keys = smem + sizeof(uint32_t) * (size_t)N + 16;
+    const int keys_in_smem = with_keys <= (size_t)227 * 1024 && N <= 15 * 4 * kNmsThreads ? 1 : 0;  // (64-bit taker masks)
+    if (keys_in_smem) smem = with_keys;
     FRCNN_CUDA(ensure_dynamic_smem<0>((const void*)nms_select_kernel, smem));
     nms_select_kernel<<<segments, kNmsThreads, smem, st>>>(boxes, keys, N, cap, top_n, iou_thr, kept_idx, kept_count,
-                                                           exhausted);
+                                                           exhausted, keys_in_smem, fin);
     FRCNN_LAUNCH_CHECK("nms_select_kernel");
     return 0;
 }
@@ -742,6 +1023,9 @@ static int postprocess_impl(float img_h, float img_w, const float* regions, int 
     int rc = launch_decode_filter(img_h, img_w, regions, regions_batched, pred_scores, logits, softmax_out, pred_boxes, B,
                                   N, nc, score_threshold, (float*)w.boxes_rel, w.keys, stream);
     if (rc) return rc;
+    if (nc == 1)  // one class per image: the NMS CTA writes the padded outputs itself (no finalize launch)
+        return launch_nms(w.boxes_rel, w.keys, B, N, cap, pre_nms_top_n, iou_threshold, w.kept_idx, w.kept_count, w.exhausted, st,
+                          NmsFinalize{(float4*)out_boxes, out_scores, out_classes, out_valid, out_idx, out_exhausted, max_total});
     rc = launch_nms(w.boxes_rel, w.keys, B * nc, N, cap, pre_nms_top_n, iou_threshold, w.kept_idx, w.kept_count,
                     w.exhausted, st);
     if (rc) return rc;

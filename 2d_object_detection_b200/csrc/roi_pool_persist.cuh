@@ -172,6 +172,14 @@ __device__ __forceinline__ unsigned uniform(unsigned v) { return __reduce_or_syn
 // for the round trip to L2 at the issue point: 3-4 % of the stall samples.  A float counter (atom.add.f32 is left
 // alone) removes that wait, but the time moves into the row-barrier waits: 0.1687 vs 0.1695 ms forward, 0.3434 vs
 // 0.3421 ms backward in an alternating A/B on one box -- not worth a 2^24-item limit, so the counter stays an integer.
+// The first item of a warp is static (its global warp index).  The second one is static too (index + number of warps) when
+// the launch is long -- no atom round trip before the first item -- and comes from the counter when every warp only gets a
+// few items (a batch of one image: 4800 items for 2240 warps): there the static pair fixes the makespan at the worst pair
+// of items, while handing out everything behind the first item lets the warps that drew short items take more of them.
+__host__ __device__ __forceinline__ bool second_item_is_static(int n_items, int total_warps) { return n_items >= 8 * total_warps; }
+__host__ __device__ __forceinline__ unsigned first_ticket(int n_items, int total_warps) {
+    return (second_item_is_static(n_items, total_warps) ? 2u : 1u) * (unsigned)total_warps;
+}
 __device__ __forceinline__ unsigned take_ticket(unsigned* counter) {
     unsigned t;
     asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(counter) : "memory");
@@ -230,7 +238,7 @@ __global__ void __launch_bounds__(kPThreads, 1)
     }
     __syncwarp();
     const int total_warps = gridDim.x * kPWarps;
-    int idx_cur = blockIdx.x * kPWarps + warp;  // the first two items are static; the counter starts at 2 * total_warps
+    int idx_cur = blockIdx.x * kPWarps + warp;  // the first item (or two: second_item_is_static) is static
     int idx_nxt = idx_cur + total_warps;
     if (idx_cur >= n_items) return;
     const float onef = kOne;
@@ -265,8 +273,12 @@ __global__ void __launch_bounds__(kPThreads, 1)
     int half = 0;
     bool prefetched = false;
     fetch_record(idx_cur, 0);
-    if (idx_nxt < n_items) fetch_record(idx_nxt, 1);
     unsigned ticket = 0u;                      // lane 0: index of the item after next (an atomicAdd in flight)
+    if (!second_item_is_static(n_items, total_warps)) {  // (the round trip overlaps the fetch of the first record)
+        if (lane == 0) ticket = take_ticket(counter);
+        idx_nxt = (int)uniform(lane == 0 ? ticket : 0u);
+    }
+    if (idx_nxt < n_items) fetch_record(idx_nxt, 1);
     if (lane == 0) ticket = take_ticket(counter);
     mbar_wait(bar_s + kRowBars * 8, 0u);       // the first record
     rec_phase = 1u;

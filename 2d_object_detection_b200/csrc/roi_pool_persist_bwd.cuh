@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(kPThreads, 1)
     }
     __syncwarp();
     const int total_warps = gridDim.x * kPWarps;
-    int idx_cur = blockIdx.x * kPWarps + warp;  // the first two items are static; the counter starts at 2 * total_warps
+    int idx_cur = blockIdx.x * kPWarps + warp;  // the first item (or two: second_item_is_static) is static
     int idx_nxt = idx_cur + total_warps;
     if (idx_cur >= n_items) return;
 
@@ -69,6 +69,10 @@ __global__ void __launch_bounds__(kPThreads, 1)
     int dslot = 0, buf = 0;
     fetch_record(idx_cur, 0);
     unsigned ticket = 0u;
+    if (!second_item_is_static(n_items, total_warps)) {  // few items per warp: the second one comes from the counter too
+        if (lane == 0) ticket = take_ticket(counter);
+        idx_nxt = (int)uniform(lane == 0 ? ticket : 0u);
+    }
     if (lane == 0) ticket = take_ticket(counter);
     {  // cold start of the stream of bin-rows
         const int roi = idx_cur / nch, ch0 = (idx_cur - roi * nch) * kWarpCh;

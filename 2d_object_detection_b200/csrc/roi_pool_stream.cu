@@ -512,7 +512,7 @@ int launch_roi_pool_fwd_persist(const float* feat, int B, int Hf, int Wf, int C,
     const int budget = g_roi_pool_max_sms.load(std::memory_order_relaxed);
     const int ctas = min((n_items + kPWarps - 1) / kPWarps, budget > 0 ? min(budget, sms) : sms);  // one CTA per SM
     roi_records_kernel<<<(n_rois + 3) / 4, 128, 0, st>>>((const float4*)rois, n_rois, R, Hf, Wf, recs, counter,
-                                                        2u * (unsigned)(ctas * kPWarps));
+                                                        first_ticket(n_items, ctas * kPWarps));
     FRCNN_LAUNCH_CHECK("roi_records_kernel");
     if (codes) {
         if (C == 1024) roi_pool_fwd_persist_kernel<1024, true><<<ctas, kPThreads, smem, st>>>(*maps, feat, Hf, Wf, C, recs, n_items, out, codes, counter);
@@ -557,7 +557,7 @@ int launch_roi_pool_bwd_persist(int B, int Hf, int Wf, int C, const float* rois,
     const int budget = g_roi_pool_max_sms.load(std::memory_order_relaxed);
     const int ctas = min((n_items + kPWarps - 1) / kPWarps, budget > 0 ? min(budget, sms) : sms);
     roi_records_kernel<<<(n_rois + 3) / 4, 128, 0, st>>>((const float4*)rois, n_rois, R, Hf, Wf, recs, counter,
-                                                        2u * (unsigned)(ctas * kPWarps));
+                                                        first_ticket(n_items, ctas * kPWarps));
     FRCNN_LAUNCH_CHECK("roi_records_kernel");
     roi_pool_bwd_persist_kernel<<<ctas, kPThreads, smem, st>>>(*maps, Hf, Wf, C, recs, n_items, dy, codes, dfeat, counter);
     FRCNN_LAUNCH_CHECK("roi_pool_bwd_persist_kernel");

@@ -14,7 +14,7 @@ class ProposalRoIEngine:
     another.  The proposal buffers are double-buffered and guarded by events, so results are identical to the
     serial order.  ``overlap=False`` issues everything on the current stream (latency measurement)."""
 
-    KERNELS_PER_STEP = 5  # decode_filter, nms_select, finalize, roi_records, roi_pool_fwd
+    KERNELS_PER_STEP = 4  # decode_filter, nms_select (writes the padded single-class outputs itself), roi_records, roi_pool_fwd
 
     def __init__(self, image_shape, batch, grid_shape, channels, num_anchors, score_threshold, iou_threshold,
                  max_total_size, pooled_size=7, kernel_size=2, pre_nms_top_n=None, overlap=True, reserve_sms=None):
@@ -156,7 +156,7 @@ class TrainStepEngine:
     features and the RCNN predictions are the caller's: ``rcnn_scores`` / ``rcnn_boxes`` / ``d_pooled`` are its tensors
     (bench.py passes synthetic ones)."""
 
-    KERNELS_PER_STEP = 19  # 2 gathers, 3 postprocess, 2+1 RPN targets/samples, 1 loss, 2 pool fwd (records + pool), 1 scale, 2+1 RCNN, 1 loss, 2 pool bwd (records + pool) (+ 3 memsets)
+    KERNELS_PER_STEP = 18  # 2 gathers, 2 postprocess (decode_filter + nms_select; one class: no finalize launch), 2+1 RPN targets/samples, 1 loss, 2 pool fwd (records + pool), 1 scale, 2+1 RCNN, 1 loss, 2 pool bwd (records + pool) (+ 3 memsets)
 
     def __init__(self, image_shape, batch, grid_shape, channels, anchors, num_classes, rpn_config, rcnn_config,
                  max_num_objects=100, pre_nms_top_n=None):

@@ -450,7 +450,7 @@ def measure_inference(ctx, w, syn, steps, warmup, min_seconds, with_e2e, e2e_sec
                      "alone_burst": {"kernel_ms": burst_ms, "achieved": alg["roi_pool_fwd"] / (burst_ms * 1e-3) / 1e9,
                                      "frac": alg["roi_pool_fwd"] / (burst_ms * 1e-3) / 1e9 / ctx.peak_gbs,
                                      "how": "records + pool kernel alone on all SMs, 10 launches after a 0.25 s pause, median"},
-                     "other_kernels": "decode_filter / nms_select / finalize: latency-bound by size (a few MB per launch, "
+                     "other_kernels": "decode_filter / nms_select (+ fused single-class finalize): latency-bound by size (a few MB per launch, "
                                       "one CTA per image for NMS), overlapped with the RoI pool of the previous step"},
         "gpu_launches": eng.KERNELS_PER_STEP * steps * reps,
         "stage_algorithmic_bytes_per_step": alg,
