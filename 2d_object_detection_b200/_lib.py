@@ -47,6 +47,9 @@ SIGNATURES = {
     "frcnn_roi_pool_set_max_sms": (_i, [_i]),
     "frcnn_roi_pool_forward": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _i, _p, _p, _sz, _p]),
     "frcnn_roi_pool_backward": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _i, _p, _p, _p]),
+    "frcnn_roi_pool_prepare": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _sz, _p]),
+    "frcnn_roi_pool_forward_prepared": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
+    "frcnn_roi_pool_backward_prepared": (_i, [_i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
     "frcnn_roi_pool_argmax_supported": (_i, [_i, _i, _i]),
     "frcnn_roi_pool_forward_argmax": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _i, _p, _p, _p, _sz, _p]),
     "frcnn_roi_pool_backward_argmax": (_i, [_i, _i, _i, _i, _p, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),

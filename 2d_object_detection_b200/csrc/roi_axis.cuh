@@ -38,12 +38,17 @@ bool roi_pool_stream_supported(int C, int P, int k);
 // codes != nullptr: training forward, also writes the arg-max codes ([B,R,P,P,C/4] bytes).
 size_t roi_pool_stream_workspace_bytes(int B, int R);
 void roi_pool_set_max_sms(int max_sms);
+// prepared: the workspace already holds the records of `rois` and fresh counters (launch_roi_records ran before, possibly
+// on another stream the caller has ordered this one after) -- only the pooling kernel is launched and `rois` is not read.
+int launch_roi_records(int B, int Hf, int Wf, const float* rois, int R, void* workspace, size_t workspace_bytes, cudaStream_t st);
 int launch_roi_pool_fwd_persist(const float* feat, int B, int Hf, int Wf, int C, const float* rois, int R, float* out,
-                                unsigned char* codes, void* workspace, size_t workspace_bytes, cudaStream_t st);
+                                unsigned char* codes, void* workspace, size_t workspace_bytes, cudaStream_t st,
+                                bool prepared = false);
 
 // Backward from the saved arg-max codes on the same walk (TMA reduce-add rows); dfeat must already be zeroed.
 
 int launch_roi_pool_bwd_persist(int B, int Hf, int Wf, int C, const float* rois, int R, const float* dy,
-                                const unsigned char* codes, float* dfeat, void* workspace, size_t workspace_bytes, cudaStream_t st);
+                                const unsigned char* codes, float* dfeat, void* workspace, size_t workspace_bytes, cudaStream_t st,
+                                bool prepared = false);
 
 }  // namespace frcnn

@@ -844,6 +844,42 @@ int frcnn_roi_pool_backward(const float* feat, int B, int Hf, int Wf, int C, con
     return 0;
 }
 
+int frcnn_roi_pool_prepare(const float* rois, int B, int R, int Hf, int Wf, int C, int P, int k, void* workspace,
+                           size_t workspace_bytes, frcnn_stream_t stream) {
+    FRCNN_REQUIRE(B > 0 && Hf > 0 && Wf > 0 && C > 0 && R >= 0 && B <= 65535, FRCNN_EINVAL, "roi_pool_prepare: bad shape");
+    FRCNN_REQUIRE(roi_pool_stream_supported(C, P, k) && !kForceBinRowWalk, FRCNN_EINVAL,
+                  "roi_pool_prepare: only the row-streaming configuration (pooled_size 7, kernel_size 2, C %% 512 == 0) has records");
+    FRCNN_REQUIRE(aligned16(rois), FRCNN_EINVAL, "roi_pool_prepare: rois must be 16-byte aligned");
+    if (R == 0) return 0;
+    return launch_roi_records(B, Hf, Wf, rois, R, workspace, workspace_bytes, as_stream(stream));
+}
+
+int frcnn_roi_pool_forward_prepared(const float* feat, int B, int Hf, int Wf, int C, int R, int P, int k, float* out,
+                                    unsigned char* argmax_codes, void* workspace, size_t workspace_bytes,
+                                    frcnn_stream_t stream) {
+    FRCNN_REQUIRE(B > 0 && Hf > 0 && Wf > 0 && C > 0 && R >= 0 && B <= 65535, FRCNN_EINVAL, "roi_pool_forward_prepared: bad shape");
+    FRCNN_REQUIRE(roi_pool_stream_supported(C, P, k) && !kForceBinRowWalk, FRCNN_EINVAL,
+                  "roi_pool_forward_prepared: only the row-streaming configuration has records");
+    FRCNN_REQUIRE(aligned16(feat) && aligned16(out), FRCNN_EINVAL, "roi_pool_forward_prepared: pointers must be 16-byte aligned");
+    if (R == 0) return 0;
+    return launch_roi_pool_fwd_persist(feat, B, Hf, Wf, C, nullptr, R, out, argmax_codes, workspace, workspace_bytes,
+                                       as_stream(stream), true);
+}
+
+int frcnn_roi_pool_backward_prepared(int B, int Hf, int Wf, int C, int R, int P, int k, const float* dy,
+                                     const unsigned char* argmax_codes, float* dfeat, void* workspace, size_t workspace_bytes,
+                                     frcnn_stream_t stream) {
+    FRCNN_REQUIRE(B > 0 && Hf > 0 && Wf > 0 && C > 0 && R >= 0 && B <= 65535, FRCNN_EINVAL, "roi_pool_backward_prepared: bad shape");
+    FRCNN_REQUIRE(roi_pool_stream_supported(C, P, k) && !kForceBinRowWalk, FRCNN_EINVAL,
+                  "roi_pool_backward_prepared: only the row-streaming configuration has records");
+    FRCNN_REQUIRE(aligned16(dy) && aligned16(dfeat) && argmax_codes, FRCNN_EINVAL,
+                  "roi_pool_backward_prepared: pointers must be 16-byte aligned");
+    FRCNN_CUDA(cudaMemsetAsync(dfeat, 0, sizeof(float) * (size_t)B * Hf * Wf * C, as_stream(stream)));
+    if (R == 0) return 0;
+    return launch_roi_pool_bwd_persist(B, Hf, Wf, C, nullptr, R, dy, argmax_codes, dfeat, workspace, workspace_bytes,
+                                       as_stream(stream), true);
+}
+
 int frcnn_roi_pool_argmax_supported(int C, int pooled_size, int kernel_size) {
     return (C % 4 == 0 && kernel_size == 2 && pooled_size >= 1 && pooled_size <= 8) ? 1 : 0;
 }

@@ -65,11 +65,12 @@ static_assert(offsetof(RoiRecord, wx) == 0 && offsetof(RoiRecord, aoff) == 56 &&
 
 // One warp per RoI: the prologue of roi_pool_fwd_stream_kernel, once per RoI instead of once per (RoI, 256 channels) CTA.
 __global__ void __launch_bounds__(128) roi_records_kernel(const float4* __restrict__ rois, int n_rois, int R, int Hf, int Wf,
-                                                          RoiRecord* __restrict__ recs, unsigned* __restrict__ counter,
-                                                          unsigned counter_init) {
+                                                          RoiRecord* __restrict__ recs, unsigned* __restrict__ counter) {
     const int lane = threadIdx.x & 31, gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const unsigned all = 0xffffffffu;
-    if (gw == 0 && lane == 0) *counter = counter_init;  // the work counter of the pooling kernel that follows on the stream
+    // the work counters of the pooling kernels that follow on the stream (word 0: forward, word 1: backward); tickets count
+    // from 0, a kernel adds the number of items it hands out statically (first_ticket: depends on its own grid)
+    if (gw == 0 && lane < 2) counter[lane] = 0u;
     if (gw >= n_rois) return;
     const int b = gw / R;
     const float4 roi = rois[gw];  // x1,y1,x2,y2 (fast_rcnn_detector.py:157-158 reorders for TF)
@@ -274,12 +275,13 @@ __global__ void __launch_bounds__(kPThreads, 1)
     bool prefetched = false;
     fetch_record(idx_cur, 0);
     unsigned ticket = 0u;                      // lane 0: index of the item after next (an atomicAdd in flight)
+    const unsigned ticket0 = first_ticket(n_items, total_warps);  // tickets count from 0: item = ticket + ticket0
     if (!second_item_is_static(n_items, total_warps)) {  // (the round trip overlaps the fetch of the first record)
-        if (lane == 0) ticket = take_ticket(counter);
+        if (lane == 0) ticket = take_ticket(counter) + ticket0;
         idx_nxt = (int)uniform(lane == 0 ? ticket : 0u);
     }
     if (idx_nxt < n_items) fetch_record(idx_nxt, 1);
-    if (lane == 0) ticket = take_ticket(counter);
+    if (lane == 0) ticket = take_ticket(counter) + ticket0;
     mbar_wait(bar_s + kRowBars * 8, 0u);       // the first record
     rec_phase = 1u;
 
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(kPThreads, 1)
         if (idx_nxt < n_items) {
             if (idx_n2 < n_items) {
                 fetch_record(idx_n2, n2buf);
-                if (lane == 0) ticket = take_ticket(counter);
+                if (lane == 0) ticket = take_ticket(counter) + ticket0;
             }
             mbar_wait(bar_s + (kRowBars + nbuf) * 8, (rec_phase >> nbuf) & 1u);  // fetched one item ago: normally complete
             rec_phase ^= 1u << nbuf;

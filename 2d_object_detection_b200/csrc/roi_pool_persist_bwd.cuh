@@ -69,11 +69,12 @@ __global__ void __launch_bounds__(kPThreads, 1)
     int dslot = 0, buf = 0;
     fetch_record(idx_cur, 0);
     unsigned ticket = 0u;
+    const unsigned ticket0 = first_ticket(n_items, total_warps);  // tickets count from 0: item = ticket + ticket0
     if (!second_item_is_static(n_items, total_warps)) {  // few items per warp: the second one comes from the counter too
-        if (lane == 0) ticket = take_ticket(counter);
+        if (lane == 0) ticket = take_ticket(counter) + ticket0;
         idx_nxt = (int)uniform(lane == 0 ? ticket : 0u);
     }
-    if (lane == 0) ticket = take_ticket(counter);
+    if (lane == 0) ticket = take_ticket(counter) + ticket0;
     {  // cold start of the stream of bin-rows
         const int roi = idx_cur / nch, ch0 = (idx_cur - roi * nch) * kWarpCh;
 #pragma unroll 1
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(kPThreads, 1)
         const bool has_next = idx_nxt < n_items;
         if (has_next) {
             fetch_record(idx_nxt, buf ^ 1);
-            if (idx_n2 < n_items && lane == 0) ticket = take_ticket(counter);
+            if (idx_n2 < n_items && lane == 0) ticket = take_ticket(counter) + ticket0;
         }
         const unsigned rec = rec_s + buf * kRecBytes;
         const unsigned f = uniform(lds_u32(rec + 184)), g8 = uniform(lds_u32(rec + 188));

@@ -478,9 +478,24 @@ void roi_pool_set_max_sms(int max_sms) { g_roi_pool_max_sms.store(max_sms > 0 ? 
 
 size_t roi_pool_stream_workspace_bytes(int B, int R) { return 256 + (size_t)kRecStride * (size_t)B * (size_t)R; }
 
-// Persistent forward: records pre-kernel + warp-persistent pooling kernel.  workspace: [counter | records].
+// The records pre-kernel alone (frcnn_roi_pool_prepare): a caller that pipelines steps runs it with the proposal path, off
+// the pooling stream, and launches the pooling kernels with mode kPoolPrepared.
+int launch_roi_records(int B, int Hf, int Wf, const float* rois, int R, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    FRCNN_REQUIRE(workspace && workspace_bytes >= roi_pool_stream_workspace_bytes(B, R) && aligned16(workspace), FRCNN_EWORKSPACE,
+                  "roi_pool_prepare: workspace too small (frcnn_roi_pool_workspace_bytes)");
+    FRCNN_REQUIRE(Hf <= 65535 && Wf <= 65535, FRCNN_ELIMIT, "roi_pool_prepare: feature map side beyond 65535");
+    unsigned* counter = static_cast<unsigned*>(workspace);
+    RoiRecord* recs = reinterpret_cast<RoiRecord*>(static_cast<unsigned char*>(workspace) + 256);
+    const int n_rois = B * R;
+    roi_records_kernel<<<(n_rois + 3) / 4, 128, 0, st>>>((const float4*)rois, n_rois, R, Hf, Wf, recs, counter);
+    FRCNN_LAUNCH_CHECK("roi_records_kernel");
+    return 0;
+}
+
+// Persistent forward: records pre-kernel (unless prepared: the workspace already holds this batch's records and fresh
+// counters) + warp-persistent pooling kernel.  workspace: [forward counter, backward counter | records].
 int launch_roi_pool_fwd_persist(const float* feat, int B, int Hf, int Wf, int C, const float* rois, int R, float* out,
-                                unsigned char* codes, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                                unsigned char* codes, void* workspace, size_t workspace_bytes, cudaStream_t st, bool prepared) {
     FRCNN_REQUIRE(workspace && workspace_bytes >= roi_pool_stream_workspace_bytes(B, R) && aligned16(workspace), FRCNN_EWORKSPACE,
                   "roi_pool_forward: workspace too small (frcnn_roi_pool_workspace_bytes)");
     FRCNN_REQUIRE(Hf <= 65535 && Wf <= 65535, FRCNN_ELIMIT, "roi_pool_forward: feature map side beyond 65535");
@@ -511,9 +526,10 @@ int launch_roi_pool_fwd_persist(const float* feat, int B, int Hf, int Wf, int C,
     const int n_rois = B * R, n_items = n_rois * (C / kWarpCh);
     const int budget = g_roi_pool_max_sms.load(std::memory_order_relaxed);
     const int ctas = min((n_items + kPWarps - 1) / kPWarps, budget > 0 ? min(budget, sms) : sms);  // one CTA per SM
-    roi_records_kernel<<<(n_rois + 3) / 4, 128, 0, st>>>((const float4*)rois, n_rois, R, Hf, Wf, recs, counter,
-                                                        first_ticket(n_items, ctas * kPWarps));
-    FRCNN_LAUNCH_CHECK("roi_records_kernel");
+    if (!prepared) {
+        roi_records_kernel<<<(n_rois + 3) / 4, 128, 0, st>>>((const float4*)rois, n_rois, R, Hf, Wf, recs, counter);
+        FRCNN_LAUNCH_CHECK("roi_records_kernel");
+    }
     if (codes) {
         if (C == 1024) roi_pool_fwd_persist_kernel<1024, true><<<ctas, kPThreads, smem, st>>>(*maps, feat, Hf, Wf, C, recs, n_items, out, codes, counter);
         else roi_pool_fwd_persist_kernel<0, true><<<ctas, kPThreads, smem, st>>>(*maps, feat, Hf, Wf, C, recs, n_items, out, codes, counter);
@@ -527,7 +543,8 @@ int launch_roi_pool_fwd_persist(const float* feat, int B, int Hf, int Wf, int C,
 
 // Persistent backward: records pre-kernel + warp-persistent kernel.  dfeat must have been zeroed on the same stream.
 int launch_roi_pool_bwd_persist(int B, int Hf, int Wf, int C, const float* rois, int R, const float* dy,
-                                const unsigned char* codes, float* dfeat, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                                const unsigned char* codes, float* dfeat, void* workspace, size_t workspace_bytes, cudaStream_t st,
+                                bool prepared) {
     FRCNN_REQUIRE(workspace && workspace_bytes >= roi_pool_stream_workspace_bytes(B, R) && aligned16(workspace), FRCNN_EWORKSPACE,
                   "roi_pool_backward: workspace too small (frcnn_roi_pool_workspace_bytes)");
     FRCNN_REQUIRE(Hf <= 65535 && Wf <= 65535, FRCNN_ELIMIT, "roi_pool_backward: feature map side beyond 65535");
@@ -556,10 +573,11 @@ int launch_roi_pool_bwd_persist(int B, int Hf, int Wf, int C, const float* rois,
     const int n_rois = B * R, n_items = n_rois * (C / kWarpCh);
     const int budget = g_roi_pool_max_sms.load(std::memory_order_relaxed);
     const int ctas = min((n_items + kPWarps - 1) / kPWarps, budget > 0 ? min(budget, sms) : sms);
-    roi_records_kernel<<<(n_rois + 3) / 4, 128, 0, st>>>((const float4*)rois, n_rois, R, Hf, Wf, recs, counter,
-                                                        first_ticket(n_items, ctas * kPWarps));
-    FRCNN_LAUNCH_CHECK("roi_records_kernel");
-    roi_pool_bwd_persist_kernel<<<ctas, kPThreads, smem, st>>>(*maps, Hf, Wf, C, recs, n_items, dy, codes, dfeat, counter);
+    if (!prepared) {
+        roi_records_kernel<<<(n_rois + 3) / 4, 128, 0, st>>>((const float4*)rois, n_rois, R, Hf, Wf, recs, counter);
+        FRCNN_LAUNCH_CHECK("roi_records_kernel");
+    }
+    roi_pool_bwd_persist_kernel<<<ctas, kPThreads, smem, st>>>(*maps, Hf, Wf, C, recs, n_items, dy, codes, dfeat, counter + 1);
     FRCNN_LAUNCH_CHECK("roi_pool_bwd_persist_kernel");
     return 0;
 }

@@ -29,8 +29,11 @@ class ProposalRoIEngine:
         # The persistent RoI kernel takes one CTA per SM; the proposal path of the next step (one 1024-thread NMS CTA per
         # image) needs whole SMs to run beside it, so the pipelined engine keeps `reserve_sms` SMs out of the pool's grid.
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        # Half an SM per image: the proposal path of a batch then runs as two waves of NMS CTAs, ~80 us for the KITTI grid
+        # against ~170 us of pooling for the same 8 images, and the pool keeps four more SMs than with one SM per image
+        # (same-box sweep, profiles/r2_reserve_sms_sweep.txt: 46.3 k images/s with 4 reserved SMs, 45.7 k with 8).
         if reserve_sms is None:
-            reserve_sms = min(self.B, sms // 8) if self.overlap else 0
+            reserve_sms = min((self.B + 1) // 2, sms // 8) if self.overlap else 0
         self.pool_sms = max(1, sms - int(reserve_sms)) if reserve_sms else 0  # 0 = every SM
         self.ws_bytes = self._lib.frcnn_postprocess_workspace_bytes(self.B, self.N, 1, self.R, self.R)
         self.ws = torch.empty(max(self.ws_bytes, 16), dtype=torch.uint8, device=dev)
@@ -41,7 +44,10 @@ class ProposalRoIEngine:
         self._num_valid = mk(self.B, dtype=torch.int32)
         self.pooled = torch.empty((self.B, self.R, self.P, self.P, self.C), dtype=torch.float32, device=dev)
         self.pool_ws_bytes = self._lib.frcnn_roi_pool_workspace_bytes(self.B, self.R, self.C, self.P, self.k)
-        self.pool_ws = torch.empty(max(self.pool_ws_bytes, 16), dtype=torch.uint8, device=dev)  # pools run one at a time (one stream)
+        # one workspace per proposal buffer: the records of step i + 1 are built (with its proposals) while the pool of step i
+        # still reads its own
+        self._pool_ws = [torch.empty(max(self.pool_ws_bytes, 16), dtype=torch.uint8, device=dev) for _ in range(2)]
+        self._split = self.pool_ws_bytes > 0  # row-streaming configuration: records pre-kernel separate from the pooling kernel
         self._i = 0
         self.s_prop = torch.cuda.Stream(device=dev, priority=-1)  # few large CTAs: let them in ahead of the pool grid
         self.s_pool = torch.cuda.Stream(device=dev)
@@ -62,6 +68,10 @@ class ProposalRoIEngine:
     def num_valid(self):
         return self._num_valid[(self._i - 1) & 1]
 
+    @property
+    def pool_ws(self):
+        return self._pool_ws[(self._i - 1) & 1]
+
     # algorithmic bytes per step of each stage (BASELINE.md section 3 / SURVEY 8(d)), for roofline reporting
     def algorithmic_bytes(self, pre_nms=None):
         N, R, B = self.N, self.R, self.B
@@ -79,12 +89,22 @@ class ProposalRoIEngine:
                                           self.iou_threshold, self.R, self.R, self.pre_nms_top_n, ptr(self._rois[j]),
                                           ptr(self._roi_scores[j]), ptr(self._classes[j]), ptr(self._num_valid[j]),
                                           None, None, ptr(self.ws), self.ws_bytes, stream()), "postprocess_output")
+        if self._split:
+            # the per-RoI records of the pooling kernel belong to the proposal path (they only need the rois): built here,
+            # on the proposal stream, they never sit between two pooling kernels
+            check(self._lib.frcnn_roi_pool_prepare(ptr(self._rois[j]), self.B, self.R, self.Hf, self.Wf, self.C, self.P, self.k,
+                                                   ptr(self._pool_ws[j]), self.pool_ws_bytes, stream()), "roi_pool_prepare")
 
     def _pool(self, j, feature_maps):
         self._lib.frcnn_roi_pool_set_max_sms(self.pool_sms)
-        check(self._lib.frcnn_roi_pool_forward(ptr(feature_maps), self.B, self.Hf, self.Wf, self.C, ptr(self._rois[j]),
-                                               self.R, self.P, self.k, ptr(self.pooled), ptr(self.pool_ws), self.pool_ws_bytes,
-                                               stream()), "roi_pool_forward")
+        if self._split:
+            check(self._lib.frcnn_roi_pool_forward_prepared(ptr(feature_maps), self.B, self.Hf, self.Wf, self.C, self.R, self.P,
+                                                            self.k, ptr(self.pooled), None, ptr(self._pool_ws[j]),
+                                                            self.pool_ws_bytes, stream()), "roi_pool_forward_prepared")
+        else:
+            check(self._lib.frcnn_roi_pool_forward(ptr(feature_maps), self.B, self.Hf, self.Wf, self.C, ptr(self._rois[j]),
+                                                   self.R, self.P, self.k, ptr(self.pooled), ptr(self._pool_ws[j]),
+                                                   self.pool_ws_bytes, stream()), "roi_pool_forward")
 
     def reset_pipeline(self):
         """Forget the events of earlier steps (call after ``drain()`` + a synchronisation, e.g. before capturing a block of

@@ -164,6 +164,22 @@ FRCNN_API int frcnn_roi_pool_forward(const float* feature_maps, int B, int Hf, i
                            int pooled_size, int kernel_size, float* out, void* workspace, size_t workspace_bytes,
                            frcnn_stream_t stream);
 
+/* The same call in two parts, for callers that pipeline batches (engine.ProposalRoIEngine): frcnn_roi_pool_prepare builds
+ * the per-RoI records of `rois` in the workspace (the small pre-kernel; it belongs with the proposal path, which produces
+ * the rois -- fast_rcnn_detector.py:154-158 reads them once per call) and arms the workspace for ONE forward and ONE
+ * backward; frcnn_roi_pool_forward_prepared / _backward_prepared then launch only the pooling kernel (argmax_codes of the
+ * forward may be NULL: inference).  The caller orders the streams (prepare before the pooling launch) and keeps the
+ * workspace untouched in between.  Row-streaming configuration only (frcnn_roi_pool_workspace_bytes(...) > 0), else
+ * FRCNN_EINVAL.  Same bits as frcnn_roi_pool_forward / _forward_argmax / _backward_argmax. */
+FRCNN_API int frcnn_roi_pool_prepare(const float* rois, int B, int R, int Hf, int Wf, int C, int pooled_size, int kernel_size,
+                           void* workspace, size_t workspace_bytes, frcnn_stream_t stream);
+FRCNN_API int frcnn_roi_pool_forward_prepared(const float* feature_maps, int B, int Hf, int Wf, int C, int R, int pooled_size,
+                                    int kernel_size, float* out, unsigned char* argmax_codes, void* workspace,
+                                    size_t workspace_bytes, frcnn_stream_t stream);
+FRCNN_API int frcnn_roi_pool_backward_prepared(int B, int Hf, int Wf, int C, int R, int pooled_size, int kernel_size,
+                                     const float* dy, const unsigned char* argmax_codes, float* dfeature, void* workspace,
+                                     size_t workspace_bytes, frcnn_stream_t stream);
+
 /* Gradient w.r.t. feature_maps (models/faster_rcnn.py:73,103 through :168 and :160): MaxPoolGrad to
  * the first maximum in row-major window order, then CropAndResizeGradImage.  dfeature [B,Hf,Wf,C] is
  * overwritten (zero-initialised here).  No box gradient (post_processing.py:58 stop_gradient). */

@@ -132,6 +132,26 @@ def test_nms_score_ties_lower_index_first(det, orc, rng):
         np.testing.assert_array_equal(host(kept)[:int(cnt)], orc.nms(boxes, scores, 0.0, 0.5, 700, 900))
 
 
+@pytest.mark.parametrize("n", [4097, 4098, 4099, 40000, 45001])
+def test_nms_key_layouts_of_the_radix_select(det, orc, rng, n):
+    """The radix select works on keys relative to the largest key and starts below the leading bits all candidates share:
+    score sets whose keys span the whole float range, a few thousand consecutive floats (narrow last key digit), one
+    binade, with the best candidate at index 0 / at the end, for segment lengths that leave an unaligned tail
+    (n % 4 != 0) and on either side of the limit up to which a segment's keys stay in shared memory (~40 k)."""
+    xy = rng.uniform(0, 1, (n, 2))
+    boxes = np.concatenate([xy, xy + rng.uniform(0.02, 0.15, (n, 2))], -1).astype(F)
+    perm = rng.permutation(n)
+    consecutive = (np.float32(0.5).view(np.uint32) + perm.astype(np.uint32)).view(F)  # n consecutive floats above 0.5
+    wide = np.exp(rng.uniform(-80.0, 0.0, n)).astype(F)                                # 1e-35 .. 1
+    binade = (0.5 + 0.5 * rng.permutation(n) / n).astype(F)
+    first = binade.copy(); first[0] = 0.999999
+    last = binade.copy(); last[-1] = 0.999999
+    for scores in (consecutive, wide, binade, first, last):
+        for cap, top_n in ((300, None), (64, 1000)):
+            kept, cnt, _ = det.non_max_suppression(dev(boxes), dev(scores), 0.0, 0.6, cap, top_n)
+            np.testing.assert_array_equal(host(kept)[:int(cnt)], orc.nms(boxes, scores, 0.0, 0.6, cap, top_n))
+
+
 def test_nms_edge_cases(det, orc, rng):
     boxes = np.array([[0, 0, 10, 10], [1, 1, 11, 11], [20, 20, 30, 30]], F)
     scores = np.array([0.9, 0.8, 0.7], F)
@@ -915,3 +935,41 @@ def test_roi_pool_sm_budget_and_workspace_contract(det, orc, syn, rng):
     assert rc == -2 and "workspace" in det._lib.last_error()  # FRCNN_EWORKSPACE
     rc = L.frcnn_roi_pool_forward(ft.data_ptr(), 2, 24, 78, 512, rt.data_ptr(), 40, 7, 2, out.data_ptr(), None, 0, stream)
     assert rc == -2
+
+
+def test_roi_pool_prepared_calls_match_the_one_call_forms(det, orc, syn, rng):
+    """frcnn_roi_pool_prepare + _forward_prepared / _backward_prepared (records built once, off the pooling stream; one
+    forward and one backward per prepare) give the bits of frcnn_roi_pool_forward(_argmax) / the gradient of
+    _backward_argmax; shapes without records are refused."""
+    L = det._lib.load()
+    B, R, C = 2, 60, 512
+    f = syn.feature_maps(rng, B, (24, 78), C)
+    rois = syn.random_rois(rng, B, R, num_valid=[51, 60])
+    ref = orc.roi_pool_forward(f, rois, 7, 2)
+    dy = rng.standard_normal(ref.shape).astype(F)
+    gref = orc.roi_pool_backward(f, rois, dy, 7, 2)
+    ft, rt, dyt = dev(f), dev(rois), dev(dy)
+    need = L.frcnn_roi_pool_workspace_bytes(B, R, C, 7, 2)
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    out = torch.empty((B, R, 7, 7, C), device="cuda")
+    codes = torch.empty((B, R, 7, 7, C // 4), dtype=torch.uint8, device="cuda")
+    dfeat = torch.full((B, 24, 78, C), 7.0, device="cuda")  # (overwritten: zero-initialised by the call)
+    s = torch.cuda.current_stream().cuda_stream
+    side = torch.cuda.Stream()
+    for with_codes in (False, True):
+        with torch.cuda.stream(side):  # the records come from another stream, as in the pipelined engine
+            assert L.frcnn_roi_pool_prepare(rt.data_ptr(), B, R, 24, 78, C, 7, 2, ws.data_ptr(), need, side.cuda_stream) == 0
+        torch.cuda.current_stream().wait_stream(side)
+        out.zero_()
+        rc = L.frcnn_roi_pool_forward_prepared(ft.data_ptr(), B, 24, 78, C, R, 7, 2, out.data_ptr(),
+                                               codes.data_ptr() if with_codes else None, ws.data_ptr(), need, s)
+        assert rc == 0, det._lib.last_error()
+        np.testing.assert_array_equal(host(out), ref)
+    rc = L.frcnn_roi_pool_backward_prepared(B, 24, 78, C, R, 7, 2, dyt.data_ptr(), codes.data_ptr(), dfeat.data_ptr(),
+                                            ws.data_ptr(), need, s)
+    assert rc == 0, det._lib.last_error()
+    np.testing.assert_allclose(host(dfeat), gref, rtol=RTOL, atol=RTOL * np.abs(gref).max())
+    g2 = host(det.roi_pool_backward_argmax(f.shape, rt, dyt, codes, 7, 2))
+    np.testing.assert_allclose(host(dfeat), g2, rtol=RTOL, atol=RTOL * np.abs(gref).max())
+    assert L.frcnn_roi_pool_prepare(rt.data_ptr(), B, R, 24, 78, 64, 7, 2, ws.data_ptr(), need, s) == -1  # C = 64: no records
+    assert L.frcnn_roi_pool_prepare(rt.data_ptr(), B, R, 24, 78, C, 7, 2, ws.data_ptr(), need - 512, s) == -2
