@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Generate tests/golden/reference_exec.npz by EXECUTING THE REFERENCE'S OWN PYTHON SOURCE on small seeded inputs.
 
-STATUS: NOT YET RUN (attempted in rounds 1 and 2; the build sandbox's security classifier refuses to execute modules from
+STATUS: NOT YET RUN (attempted in round 1 and in both sessions of round 2; the build sandbox's security classifier refuses to execute modules from
 the external reference tree without a human's authorisation -- DESIGN.md section 2 quotes the refusal).  This script is
 the prepared recipe for a maintainer who may run it.  tests/test_reference_golden.py skips
 until reference_exec.npz exists.
