@@ -386,6 +386,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
 #endif
 
     const NmsThreshold nthr = NmsThreshold::make(iou_thr);
+    const bool key32_vec = (reinterpret_cast<uintptr_t>(hist) & 15u) == 0;  // (cap % 4 == 0: the usual 300 / 1000)
 
     while (true) {
         // ===================== SELECT ===================================================================
@@ -630,13 +631,69 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
         NMS_TICK(13);
         int p2 = 32;
         while (p2 < m) p2 <<= 1;
+        // ===================== SORT descending (bitonic network) ========================================
+        // Exchanges at distance >= 32 go through shared memory (one barrier each); the distances 16 .. 1 that end every
+        // phase stay inside a warp and run on registers with shuffles -- 19 barriers instead of 45 for 512 candidates.
+        //
+        // Short lists (the usual 512-candidate refill) are not sent through the network at all: every key of the list lies
+        // in [key half of thresh, key half of hi], normally a few hundred thousand key values, so (key - base + 1) << 9 | slot
+        // fits a 32-bit word and orders the list whenever no two candidates share a key.  Those words are RANKED BY
+        // COUNTING: two threads per candidate count the words above theirs in one half of the list each (broadcast 128-bit
+        // loads, a compare and an add per word: 512 x 512 compares on 1024 threads), the rank is where the candidate's
+        // composite goes.  No barrier, no dependent shuffle chain; 19 barriers and 45 exchange steps otherwise.  Equal keys
+        // (their order is the index order the composite carries) show up as neighbours with the same key half and send the
+        // list through the 64-bit network instead.
+        const unsigned long long* sorted = comp;
+        bool sorted_done = false;
+        const unsigned int base_k = (unsigned int)(thresh >> 32);
+        if (m <= 512 && (unsigned int)(hi >> 32) - base_k < (1u << 23) - 2u) {  // (uniform)
+            unsigned int* key32 = hist;  // (the histogram is dead until the next refill; 16-byte aligned? see below)
+            unsigned long long* comp2 = reinterpret_cast<unsigned long long*>(
+                (reinterpret_cast<uintptr_t>(hist + 512) + 7) & ~static_cast<uintptr_t>(7));
+            if (tid < 512)
+                key32[tid] = tid < m ? ((((unsigned int)(comp[tid] >> 32) - base_k + 1u) << 9) | (unsigned int)tid) : 0u;
+            __syncthreads();
+            NMS_TICK(1);
+            {
+                const int e = tid >> 1, h = tid & 1;
+                const unsigned int mine = key32[e];  // (0 for e >= m: counts everything, never used)
+                const int mh = ((m + 7) >> 3) << 2;   // words per half, a multiple of 4 (the list is zero-padded to 512)
+                const unsigned int* half = key32 + mh * h;
+                unsigned int c0 = 0u, c1 = 0u, c2 = 0u, c3 = 0u;  // four independent counters: no dependent chain
+                auto count = [&](unsigned int& c, unsigned int q) {  // one compare + one guarded add
+                    asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, %2;\n\t@p add.u32 %0, %0, 1;\n\t}" : "+r"(c) : "r"(q), "r"(mine));
+                };
+#pragma unroll 4
+                for (int u = 0; u < mh; u += 4) {
+                    // (four words per load; hist is only 4-byte aligned in general, so plain 32-bit loads when it is not)
+                    unsigned int q0, q1, q2, q3;
+                    if (key32_vec) {
+                        const uint4 q = *reinterpret_cast<const uint4*>(half + u);
+                        q0 = q.x; q1 = q.y; q2 = q.z; q3 = q.w;
+                    } else {
+                        q0 = half[u]; q1 = half[u + 1]; q2 = half[u + 2]; q3 = half[u + 3];
+                    }
+                    count(c0, q0);
+                    count(c1, q1);
+                    count(c2, q2);
+                    count(c3, q3);
+                }
+                int above = (int)(c0 + c1 + c2 + c3);
+                above += __shfl_xor_sync(0xffffffffu, above, 1);
+                if (h == 0 && e < m) comp2[above] = comp[e];
+            }
+            __syncthreads();
+            const bool tie = tid > 0 && tid < m && (unsigned int)(comp2[tid] >> 32) == (unsigned int)(comp2[tid - 1] >> 32);
+            if (!__syncthreads_or(tie ? 1 : 0)) {
+                sorted = comp2;
+                sorted_done = true;
+            }
+        }
+        if (!sorted_done) {
         for (int i = m + tid; i < p2; i += kNmsThreads) comp[i] = 0ull;
         __syncthreads();
 
         NMS_TICK(1);
-        // ===================== SORT descending (bitonic network) ========================================
-        // Exchanges at distance >= 32 go through shared memory (one barrier each); the distances 16 .. 1 that end every
-        // phase stay inside a warp and run on registers with shuffles -- 19 barriers instead of 45 for 512 candidates.
         for (int k = 2; k <= p2; k <<= 1) {
             int j = k >> 1;
             for (; j >= 32; j >>= 1) {
@@ -665,10 +722,11 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
             }
             __syncthreads();
         }
+        }
 
         NMS_TICK(2);
       for (int sub = 0; sub < m && S->kept < cap; sub += kChunk) {  // (uniform: S->kept is written before a barrier)
-        const unsigned long long* scomp = comp + sub;
+        const unsigned long long* scomp = sorted + sub;
         const int ms = min(kChunk, m - sub);
         // ===================== LOAD boxes (corner-normalised) + areas of the sub-chunk ==================
         if (tid < ms) {
@@ -781,7 +839,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
         NMS_TICK(4);
       }
         if (tid == 0) {
-            S->hi = comp[m - 1];
+            S->hi = sorted[m - 1];
             S->budget -= m;
             S->remaining -= m;
             int stop = 0;
