@@ -876,6 +876,10 @@ int frcnn_roi_pool_backward_prepared(int B, int Hf, int Wf, int C, int R, int P,
                   "roi_pool_backward_prepared: pointers must be 16-byte aligned");
     FRCNN_CUDA(cudaMemsetAsync(dfeat, 0, sizeof(float) * (size_t)B * Hf * Wf * C, as_stream(stream)));
     if (R == 0) return 0;
+    FRCNN_REQUIRE(workspace && workspace_bytes >= 256, FRCNN_EWORKSPACE, "roi_pool_backward_prepared: workspace too small");
+    // the backward's work counter (second word of the workspace) is re-armed here, next to the zero-init of dfeature, so
+    // the same records serve any number of backward calls
+    FRCNN_CUDA(cudaMemsetAsync(static_cast<unsigned*>(workspace) + 1, 0, sizeof(unsigned), as_stream(stream)));
     return launch_roi_pool_bwd_persist(B, Hf, Wf, C, nullptr, R, dy, argmax_codes, dfeat, workspace, workspace_bytes,
                                        as_stream(stream), true);
 }

@@ -176,7 +176,7 @@ class TrainStepEngine:
     features and the RCNN predictions are the caller's: ``rcnn_scores`` / ``rcnn_boxes`` / ``d_pooled`` are its tensors
     (bench.py passes synthetic ones)."""
 
-    KERNELS_PER_STEP = 18  # 2 gathers, 2 postprocess (decode_filter + nms_select; one class: no finalize launch), 2+1 RPN targets/samples, 1 loss, 2 pool fwd (records + pool), 1 scale, 2+1 RCNN, 1 loss, 2 pool bwd (records + pool) (+ 3 memsets)
+    KERNELS_PER_STEP = 17  # 2 gathers, 2 postprocess (decode_filter + nms_select; one class: no finalize launch), 2+1 RPN targets/samples, 1 loss, 2 pool fwd (records + pool), 1 scale, 2+1 RCNN, 1 loss, 1 pool bwd (the forward's records) (+ 3 memsets)
 
     def __init__(self, image_shape, batch, grid_shape, channels, anchors, num_classes, rpn_config, rcnn_config,
                  max_num_objects=100, pre_nms_top_n=None):
@@ -268,9 +268,16 @@ class TrainStepEngine:
                                                    stream()), "generate_targets")
         self._samples(self.rpn_tl, self.rpn_tb, Nv, 2, sm, self.scores_v, self.deltas_v, self.rpn_samples, self.ws_smp_rpn,
                       2 * seed)
-        check(L_.frcnn_roi_pool_forward_argmax(ptr(feature_maps), B, self.Hf, self.Wf, self.C, ptr(self.rois), R, self.P, self.k,
-                                               ptr(self.pooled), ptr(self.codes), ptr(self.ws_pool[0]), self.ws_pool[1], stream()),
-              "roi_pool_forward_argmax")
+        if self.ws_pool[1] > 0:  # row-streaming configuration: one set of records serves the forward and the backward
+            check(L_.frcnn_roi_pool_prepare(ptr(self.rois), B, R, self.Hf, self.Wf, self.C, self.P, self.k, ptr(self.ws_pool[0]),
+                                            self.ws_pool[1], stream()), "roi_pool_prepare")
+            check(L_.frcnn_roi_pool_forward_prepared(ptr(feature_maps), B, self.Hf, self.Wf, self.C, R, self.P, self.k,
+                                                     ptr(self.pooled), ptr(self.codes), ptr(self.ws_pool[0]), self.ws_pool[1],
+                                                     stream()), "roi_pool_forward_prepared")
+        else:
+            check(L_.frcnn_roi_pool_forward_argmax(ptr(feature_maps), B, self.Hf, self.Wf, self.C, ptr(self.rois), R, self.P,
+                                                   self.k, ptr(self.pooled), ptr(self.codes), ptr(self.ws_pool[0]),
+                                                   self.ws_pool[1], stream()), "roi_pool_forward_argmax")
         if between is not None:
             between()  # e.g. the caller's Dense heads on self.pooled producing rcnn_scores / rcnn_boxes
         check(L_.frcnn_scale_boxes(ptr(self.rois), B * R, H, W, 0, ptr(self.rois_abs), stream()), "to_absolute")
@@ -285,9 +292,15 @@ class TrainStepEngine:
 
     def backward(self, d_pooled):
         """dL/d(pooled) [B,R,P,P,C] -> dL/d(feature_maps) from the saved arg-max codes."""
-        check(self._lib.frcnn_roi_pool_backward_argmax(self.B, self.Hf, self.Wf, self.C, ptr(self.rois), self.R, self.P, self.k,
-                                                       ptr(d_pooled), ptr(self.codes), ptr(self.d_feature), ptr(self.ws_pool[0]),
-                                                       self.ws_pool[1], stream()), "roi_pool_backward_argmax")
+        if self.ws_pool[1] > 0:  # (the records and the backward's work counter were prepared by forward())
+            check(self._lib.frcnn_roi_pool_backward_prepared(self.B, self.Hf, self.Wf, self.C, self.R, self.P, self.k, ptr(d_pooled),
+                                                             ptr(self.codes), ptr(self.d_feature), ptr(self.ws_pool[0]),
+                                                             self.ws_pool[1], stream()), "roi_pool_backward_prepared")
+        else:
+            check(self._lib.frcnn_roi_pool_backward_argmax(self.B, self.Hf, self.Wf, self.C, ptr(self.rois), self.R, self.P,
+                                                           self.k, ptr(d_pooled), ptr(self.codes), ptr(self.d_feature),
+                                                           ptr(self.ws_pool[0]), self.ws_pool[1], stream()),
+                  "roi_pool_backward_argmax")
         return self.d_feature
 
     def step(self, pred_scores, pred_boxes, feature_maps, gt_labels, gt_boxes, rcnn_scores, rcnn_boxes, d_pooled, seed=None,

@@ -166,8 +166,8 @@ FRCNN_API int frcnn_roi_pool_forward(const float* feature_maps, int B, int Hf, i
 
 /* The same call in two parts, for callers that pipeline batches (engine.ProposalRoIEngine): frcnn_roi_pool_prepare builds
  * the per-RoI records of `rois` in the workspace (the small pre-kernel; it belongs with the proposal path, which produces
- * the rois -- fast_rcnn_detector.py:154-158 reads them once per call) and arms the workspace for ONE forward and ONE
- * backward; frcnn_roi_pool_forward_prepared / _backward_prepared then launch only the pooling kernel (argmax_codes of the
+ * the rois -- fast_rcnn_detector.py:154-158 reads them once per call) and arms the workspace for ONE forward (the backward
+ * re-arms its own work counter, so it may run any number of times on the same records); frcnn_roi_pool_forward_prepared / _backward_prepared then launch only the pooling kernel (argmax_codes of the
  * forward may be NULL: inference).  The caller orders the streams (prepare before the pooling launch) and keeps the
  * workspace untouched in between.  Row-streaming configuration only (frcnn_roi_pool_workspace_bytes(...) > 0), else
  * FRCNN_EINVAL.  Same bits as frcnn_roi_pool_forward / _forward_argmax / _backward_argmax. */

@@ -969,6 +969,10 @@ def test_roi_pool_prepared_calls_match_the_one_call_forms(det, orc, syn, rng):
                                             ws.data_ptr(), need, s)
     assert rc == 0, det._lib.last_error()
     np.testing.assert_allclose(host(dfeat), gref, rtol=RTOL, atol=RTOL * np.abs(gref).max())
+    dfeat.fill_(3.0)  # a second backward on the same records (the call re-arms its work counter)
+    assert L.frcnn_roi_pool_backward_prepared(B, 24, 78, C, R, 7, 2, dyt.data_ptr(), codes.data_ptr(), dfeat.data_ptr(),
+                                              ws.data_ptr(), need, s) == 0
+    np.testing.assert_allclose(host(dfeat), gref, rtol=RTOL, atol=RTOL * np.abs(gref).max())
     g2 = host(det.roi_pool_backward_argmax(f.shape, rt, dyt, codes, 7, 2))
     np.testing.assert_allclose(host(dfeat), g2, rtol=RTOL, atol=RTOL * np.abs(gref).max())
     assert L.frcnn_roi_pool_prepare(rt.data_ptr(), B, R, 24, 78, 64, 7, 2, ws.data_ptr(), need, s) == -1  # C = 64: no records
