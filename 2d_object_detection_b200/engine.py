@@ -9,15 +9,17 @@ from ._tensor import as_device, check, lib, ptr, require_cuda, stream
 
 
 class ProposalRoIEngine:
-    """Two-stream software pipeline over steps: proposals (decode + NMS + finalize; latency-bound, a handful of
-    SMs) of step i+1 run on one stream while RoI pooling (bandwidth/ALU-bound, the whole chip) of step i runs on
-    another.  The proposal buffers are double-buffered and guarded by events, so results are identical to the
-    serial order.  ``overlap=False`` issues everything on the current stream (latency measurement)."""
+    """Software pipeline over steps: proposals (decode + NMS with its outputs + the RoI records; latency-bound, a handful
+    of SMs) of step i+1 run on one stream while RoI pooling (bandwidth/ALU-bound, the rest of the chip) of step i runs on
+    another -- on two alternating ones from four images per batch, so that consecutive pooling kernels overlap at their
+    ends.  Proposal buffers, records and pooled outputs are double-buffered and guarded by events, so results are
+    identical to the serial order.  ``overlap=False`` issues everything on the current stream (latency measurement)."""
 
     KERNELS_PER_STEP = 4  # decode_filter, nms_select (writes the padded single-class outputs itself), roi_records, roi_pool_fwd
 
     def __init__(self, image_shape, batch, grid_shape, channels, num_anchors, score_threshold, iou_threshold,
-                 max_total_size, pooled_size=7, kernel_size=2, pre_nms_top_n=None, overlap=True, reserve_sms=None):
+                 max_total_size, pooled_size=7, kernel_size=2, pre_nms_top_n=None, overlap=True, reserve_sms=None,
+                 pool_streams=None):
         dev = require_cuda()
         self.image_shape = tuple(image_shape)
         self.B, (self.Hf, self.Wf), self.C, self.N = int(batch), grid_shape, int(channels), int(num_anchors)
@@ -42,7 +44,18 @@ class ProposalRoIEngine:
         self._roi_scores = mk(self.B, self.R)
         self._classes = mk(self.B, self.R, dtype=torch.int32)
         self._num_valid = mk(self.B, dtype=torch.int32)
-        self.pooled = torch.empty((self.B, self.R, self.P, self.P, self.C), dtype=torch.float32, device=dev)
+        # Two pooling streams (and two output buffers), alternating with the proposal buffers: the pooling kernel of step
+        # i + 1 is not ordered behind the one of step i, so its CTAs start on the SMs that the CTAs of step i leave one by
+        # one -- the tail of a persistent kernel (its warps finish their last items up to one long item apart) and the ramp
+        # of the next one overlap instead of adding up (KITTI batch 8: 46.6 k -> 47.9 k images/s on one box, dense batch 16
+        # + 2 %).  Nothing else may start earlier: proposals of step i + 2 wait for pool(i) anyway.  Not for small batches:
+        # there the proposal path is the critical one and two overlapping pooling grids take its reserved SM for a while
+        # (batch 1: 22.8 k -> 20.9 k images/s), so one pooling stream below four images.
+        if pool_streams is None:
+            pool_streams = 2 if self.B >= 4 else 1
+        self.n_pool_streams = 2 if (overlap and int(pool_streams) >= 2) else 1
+        self._pooled = [torch.empty((self.B, self.R, self.P, self.P, self.C), dtype=torch.float32, device=dev)
+                        for _ in range(self.n_pool_streams)]
         self.pool_ws_bytes = self._lib.frcnn_roi_pool_workspace_bytes(self.B, self.R, self.C, self.P, self.k)
         # one workspace per proposal buffer: the records of step i + 1 are built (with its proposals) while the pool of step i
         # still reads its own
@@ -50,7 +63,7 @@ class ProposalRoIEngine:
         self._split = self.pool_ws_bytes > 0  # row-streaming configuration: records pre-kernel separate from the pooling kernel
         self._i = 0
         self.s_prop = torch.cuda.Stream(device=dev, priority=-1)  # few large CTAs: let them in ahead of the pool grid
-        self.s_pool = torch.cuda.Stream(device=dev)
+        self._s_pool = [torch.cuda.Stream(device=dev) for _ in range(self.n_pool_streams)]
         self._ev_prop = [torch.cuda.Event(), torch.cuda.Event()]
         self._ev_pool = [torch.cuda.Event(), torch.cuda.Event()]
         self._pool_recorded = [False, False]
@@ -71,6 +84,14 @@ class ProposalRoIEngine:
     @property
     def pool_ws(self):
         return self._pool_ws[(self._i - 1) & 1]
+
+    @property
+    def pooled(self):
+        return self._pooled[((self._i - 1) & 1) % self.n_pool_streams]
+
+    @property
+    def s_pool(self):
+        return self._s_pool[0]
 
     # algorithmic bytes per step of each stage (BASELINE.md section 3 / SURVEY 8(d)), for roofline reporting
     def algorithmic_bytes(self, pre_nms=None):
@@ -99,12 +120,13 @@ class ProposalRoIEngine:
         self._lib.frcnn_roi_pool_set_max_sms(self.pool_sms)
         if self._split:
             check(self._lib.frcnn_roi_pool_forward_prepared(ptr(feature_maps), self.B, self.Hf, self.Wf, self.C, self.R, self.P,
-                                                            self.k, ptr(self.pooled), None, ptr(self._pool_ws[j]),
-                                                            self.pool_ws_bytes, stream()), "roi_pool_forward_prepared")
+                                                            self.k, ptr(self._pooled[j % self.n_pool_streams]), None,
+                                                            ptr(self._pool_ws[j]), self.pool_ws_bytes, stream()),
+                  "roi_pool_forward_prepared")
         else:
             check(self._lib.frcnn_roi_pool_forward(ptr(feature_maps), self.B, self.Hf, self.Wf, self.C, ptr(self._rois[j]),
-                                                   self.R, self.P, self.k, ptr(self.pooled), ptr(self._pool_ws[j]),
-                                                   self.pool_ws_bytes, stream()), "roi_pool_forward")
+                                                   self.R, self.P, self.k, ptr(self._pooled[j % self.n_pool_streams]),
+                                                   ptr(self._pool_ws[j]), self.pool_ws_bytes, stream()), "roi_pool_forward")
 
     def reset_pipeline(self):
         """Forget the events of earlier steps (call after ``drain()`` + a synchronisation, e.g. before capturing a block of
@@ -117,12 +139,13 @@ class ProposalRoIEngine:
         ev = torch.cuda.Event()
         ev.record()
         self.s_prop.wait_event(ev)
-        self.s_pool.wait_event(ev)
+        for sp in self._s_pool:
+            sp.wait_event(ev)
 
     def drain(self):
         """Make the caller's current stream wait for everything issued so far."""
         cur = torch.cuda.current_stream()
-        for s in (self.s_prop, self.s_pool):
+        for s in (self.s_prop, *self._s_pool):
             ev = torch.cuda.Event()
             ev.record(s)
             cur.wait_event(ev)
@@ -140,22 +163,23 @@ class ProposalRoIEngine:
             self._pool(j, feature_maps)
             if pool_events:
                 pool_events[1].record()
-            return self._rois[j], self._roi_scores[j], self._num_valid[j], self.pooled
+            return self._rois[j], self._roi_scores[j], self._num_valid[j], self._pooled[0]
         if self._pool_recorded[j]:  # proposals(i) may overwrite buffer j only after pool(i-2) has read it
             self.s_prop.wait_event(self._ev_pool[j])
         with torch.cuda.stream(self.s_prop):
             self._proposals(j, regions, pred_scores, pred_boxes)
             self._ev_prop[j].record(self.s_prop)
-        self.s_pool.wait_event(self._ev_prop[j])
-        with torch.cuda.stream(self.s_pool):
+        sp = self._s_pool[j % self.n_pool_streams]
+        sp.wait_event(self._ev_prop[j])
+        with torch.cuda.stream(sp):
             if pool_events:
-                pool_events[0].record(self.s_pool)
+                pool_events[0].record(sp)
             self._pool(j, feature_maps)
             if pool_events:
-                pool_events[1].record(self.s_pool)
-            self._ev_pool[j].record(self.s_pool)
+                pool_events[1].record(sp)
+            self._ev_pool[j].record(sp)
         self._pool_recorded[j] = True
-        return self._rois[j], self._roi_scores[j], self._num_valid[j], self.pooled
+        return self._rois[j], self._roi_scores[j], self._num_valid[j], self._pooled[j % self.n_pool_streams]
 
 
 class TrainStepEngine:

@@ -336,7 +336,7 @@ def bind_to_gpu_numa_node(local_rank):
         return {"node": None, "bound": False, "error": repr(e)[:80]}
 
 
-def measure_inference(ctx, w, syn, steps, warmup, min_seconds, with_e2e, e2e_seconds, reserve_sms=None):
+def measure_inference(ctx, w, syn, steps, warmup, min_seconds, with_e2e, e2e_seconds, reserve_sms=None, pool_streams=None):
     torch, det = ctx.torch, ctx.det
     device, rank = ctx.device, ctx.rank
     B = w.batch
@@ -344,7 +344,7 @@ def measure_inference(ctx, w, syn, steps, warmup, min_seconds, with_e2e, e2e_sec
                                  [0, 0, w.image_shape[1], w.image_shape[0]])
     mk_engine = lambda overlap: det.engine.ProposalRoIEngine(  # noqa: E731
         w.image_shape, B, w.grid, w.channels, w.num_anchors, w.score_threshold, w.iou_threshold, w.max_total_size,
-        w.pooled_size, w.kernel_size, w.pre_nms_top_n, overlap=overlap, reserve_sms=reserve_sms)
+        w.pooled_size, w.kernel_size, w.pre_nms_top_n, overlap=overlap, reserve_sms=reserve_sms, pool_streams=pool_streams)
     eng = mk_engine(True)
     # Inputs larger than L2: rotate over n_sets input sets (each rank its own seeds = its own images)
     n_sets, set_bytes = input_sets(w)
@@ -416,7 +416,15 @@ def measure_inference(ctx, w, syn, steps, warmup, min_seconds, with_e2e, e2e_sec
     pool_events = [step(i, eng, events=True) for i in range(n_ev)]
     eng.drain()
     torch.cuda.synchronize()
-    pool_ms = float(np.mean([a.elapsed_time(b) for a, b in pool_events[min(3, n_ev - 1):]]))
+    first = min(3, n_ev - 1)
+    bracket_ms = float(np.mean([a.elapsed_time(b) for a, b in pool_events[first:]]))
+    # With two pooling streams consecutive launches overlap at their ends (the CTAs of launch i + 1 start on the SMs the CTAs
+    # of launch i leave), so the bracket of one launch contains time in which its CTAs wait for SMs that still belong to the
+    # launch before: the launches' device time is then the span from the first bracket's start to the last bracket's end
+    # divided by the launches in it (nothing else runs on those SMs).  With one stream the two agree whenever pooling bounds the
+    # step; where it does not (batch 1) the span is the step time and the bracket is the kernel.
+    span_ms = pool_events[first][0].elapsed_time(pool_events[-1][1]) / max(1, n_ev - first)
+    pool_ms = min(bracket_ms, span_ms)
     alg = eng.algorithmic_bytes()
     achieved = alg["roi_pool_fwd"] / (pool_ms * 1e-3) / 1e9
     kernel = "roi_pool_fwd_persist_kernel<1024>" if w.channels == 1024 else "roi_pool_fwd_persist_kernel"
@@ -445,6 +453,11 @@ def measure_inference(ctx, w, syn, steps, warmup, min_seconds, with_e2e, e2e_sec
         "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": ctx.peak_gbs, "unit": "GB/s",
                      "frac": achieved / ctx.peak_gbs, "traffic": load_traffic(w.name, "roi_pool_fwd"),
                      "peak_source": ctx.peak_src, "algorithmic_bytes_per_launch": alg["roi_pool_fwd"], "kernel_ms": pool_ms,
+                     "kernel_ms_how": ("span of %d launches on the two pooling streams / launches (they overlap at their ends); "
+                                       "mean of the per-launch event brackets, which include waiting for SMs of the launch "
+                                       "before: %.4f ms" % (n_ev - first, bracket_ms)) if eng.n_pool_streams == 2 else
+                                      "mean of the per-launch CUDA-event brackets on the pooling stream",
+                     "kernel_ms_bracketed": bracket_ms, "pool_streams": eng.n_pool_streams,
                      "kernel_launches_timed": n_ev, "frac_of_nominal_8TBps": achieved / 8000.0,
                      "share_of_step": pool_ms / ms_per_step,
                      "alone_burst": {"kernel_ms": burst_ms, "achieved": alg["roi_pool_fwd"] / (burst_ms * 1e-3) / 1e9,
@@ -628,7 +641,7 @@ def run_b200_arm(args, syn):
         res = measure_train(ctx, w, syn, args.steps, args.warmup, args.min_seconds)
     else:
         res = measure_inference(ctx, w, syn, args.steps, args.warmup, args.min_seconds, not args.no_e2e, args.e2e_seconds,
-                                args.reserve_sms)
+                                args.reserve_sms, args.pool_streams)
     others = []
     if not args.no_others:
         for name in ("kitti_b1", "kitti_b8", "dense_b16", "train_b16"):
@@ -664,7 +677,8 @@ def run_b200_arm(args, syn):
         "timing": (f"a CUDA graph of {args.steps} steps replayed {res.get('block_reps')} times back to back" if not train else
                    f"{res.get('steps_timed')} eager steps back to back") + "; CUDA events, barrier + synchronize on both sides, max over ranks",
         "overlap": ("weight-gradient all-reduce (second stream) overlaps the RoI-pool backward" if train else
-                    "proposals of step i+1 (stream A) overlap RoI pooling of step i (stream B); double-buffered rois"),
+                    "proposals + RoI records of step i+1 (stream A, reserved SMs) overlap RoI pooling of step i; pooling kernels "
+                    "alternate between two streams from 4 images per batch (their ends overlap); double-buffered rois / outputs"),
         "config": config_dict(w, args.gpus, train),
         "roofline": res["roofline"], "cpu_baseline": cpu_baseline, "e2e": res.get("e2e"),
         "gpu_launches": res["gpu_launches"], "clocks": res["clocks"], "host_cores": os.cpu_count(),
@@ -692,6 +706,9 @@ def main():
     ap.add_argument("--no-others", action="store_true")
     ap.add_argument("--reserve-sms", type=int, default=None,
                     help="SMs the pipelined engine keeps free of the persistent RoI kernel for the proposal path (default: per-GPU batch)")
+    ap.add_argument("--pool-streams", type=int, default=None,
+                    help="pooling streams of the pipelined engine (2: consecutive pooling kernels may overlap at their ends; "
+                         "default: 2 from four images per batch, else 1)")
     args = ap.parse_args()
     # the synthetic-input module is NumPy only; load it without importing the CUDA package on the reference arm
     import importlib.util

@@ -977,3 +977,59 @@ def test_roi_pool_prepared_calls_match_the_one_call_forms(det, orc, syn, rng):
     np.testing.assert_allclose(host(dfeat), g2, rtol=RTOL, atol=RTOL * np.abs(gref).max())
     assert L.frcnn_roi_pool_prepare(rt.data_ptr(), B, R, 24, 78, 64, 7, 2, ws.data_ptr(), need, s) == -1  # C = 64: no records
     assert L.frcnn_roi_pool_prepare(rt.data_ptr(), B, R, 24, 78, C, 7, 2, ws.data_ptr(), need - 512, s) == -2
+
+
+@pytest.mark.parametrize("pool_streams", [1, 2])
+def test_pipelined_engine_matches_the_serial_engine(det, orc, syn, pool_streams):
+    """ProposalRoIEngine with overlap (proposals of step i + 1 beside the pool of step i, records built with the proposals,
+    two pooling streams and output buffers so that consecutive pooling kernels may overlap at their ends): the buffers of the
+    last two steps hold the bits of the serial engine on the same inputs -- eagerly and replayed from one CUDA graph."""
+    w, anchors, _, _, _ = _decoded(orc, syn, "kitti_b8", 2, 31)
+    a = dev(anchors)
+    sets = []
+    for k in range(3):
+        rng = np.random.default_rng(100 + k)
+        sc, dl = syn.rpn_head_outputs(rng, 2, w.num_anchors)
+        sets.append((dev(sc), dev(dl), dev(syn.feature_maps(rng, 2, w.grid, 1024))))
+    mk = lambda overlap: det.engine.ProposalRoIEngine(w.image_shape, 2, w.grid, 1024, w.num_anchors, 0.0, 0.7, 300,  # noqa: E731
+                                                      pre_nms_top_n=2000, overlap=overlap, pool_streams=pool_streams)
+    serial = mk(False)
+    want = []
+    for k in range(3):
+        rois, _, nv, pooled = serial.step(a, *sets[k])
+        torch.cuda.synchronize()
+        want.append((rois.clone(), nv.clone(), pooled.clone()))
+    eng = mk(True)
+    assert eng.n_pool_streams == pool_streams
+    n = 7
+
+    def run():
+        outs = [eng.step(a, *sets[i % 3]) for i in range(n)]
+        eng.drain()
+        return outs
+
+    eng.attach()
+    outs = run()
+    torch.cuda.synchronize()
+    for i in (n - 2, n - 1):  # the two buffers still hold steps n - 2 and n - 1
+        rois, _, nv, pooled = outs[i]
+        assert torch.equal(rois, want[i % 3][0]) and torch.equal(nv, want[i % 3][1])
+        if pool_streams == 2 or i == n - 1:  # (one pooling stream: one output buffer, it holds the last step)
+            assert torch.equal(pooled, want[i % 3][2])
+    assert eng.pooled.data_ptr() == outs[n - 1][3].data_ptr() and eng.rois.data_ptr() == outs[n - 1][0].data_ptr()
+    eng.reset_pipeline()
+    side = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g):
+            eng.attach()
+            outs = run()
+    for t in outs[n - 1][2:] + outs[n - 2][2:]:
+        t.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    for i in (n - 2, n - 1):
+        rois, _, nv, pooled = outs[i]
+        assert torch.equal(rois, want[i % 3][0]) and torch.equal(nv, want[i % 3][1])
+        if pool_streams == 2 or i == n - 1:  # (one pooling stream: one output buffer, it holds the last step)
+            assert torch.equal(pooled, want[i % 3][2])
