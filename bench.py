@@ -460,6 +460,9 @@ def measure_inference(ctx, w, syn, steps, warmup, min_seconds, with_e2e, e2e_sec
                      "kernel_ms_bracketed": bracket_ms, "pool_streams": eng.n_pool_streams,
                      "kernel_launches_timed": n_ev, "frac_of_nominal_8TBps": achieved / 8000.0,
                      "share_of_step": pool_ms / ms_per_step,
+                     "share_of_step_note": "kernel_ms comes from the eager run with events (%.4f ms per step), ms_per_step from the "
+                                           "graph replay: pooling bounds the step, a share slightly above 1 is the eager run's "
+                                           "launch bubbles" % span_ms,
                      "alone_burst": {"kernel_ms": burst_ms, "achieved": alg["roi_pool_fwd"] / (burst_ms * 1e-3) / 1e9,
                                      "frac": alg["roi_pool_fwd"] / (burst_ms * 1e-3) / 1e9 / ctx.peak_gbs,
                                      "how": "records + pool kernel alone on all SMs, 10 launches after a 0.25 s pause, median"},
