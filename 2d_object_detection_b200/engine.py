@@ -153,15 +153,15 @@ class ProposalRoIEngine:
     def step(self, regions, pred_scores, pred_boxes, feature_maps, pool_events=None):
         """All arguments: fp32 contiguous CUDA tensors of the constructor's shapes.  Returns the buffers the results
         land in (rois, roi_scores, num_valid, pooled); with overlap they are complete once ``drain()``-ed.
-        ``pool_events`` = (start, end) torch events recorded around the RoI-pool launch on its stream."""
+        ``pool_events`` = (start, end) torch events recorded around the RoI-pool launch on its stream (either may be None)."""
         j = self._i & 1
         self._i += 1
         if not self.overlap:
             self._proposals(j, regions, pred_scores, pred_boxes)
-            if pool_events:
+            if pool_events and pool_events[0] is not None:
                 pool_events[0].record()
             self._pool(j, feature_maps)
-            if pool_events:
+            if pool_events and pool_events[1] is not None:
                 pool_events[1].record()
             return self._rois[j], self._roi_scores[j], self._num_valid[j], self._pooled[0]
         if self._pool_recorded[j]:  # proposals(i) may overwrite buffer j only after pool(i-2) has read it
@@ -172,10 +172,10 @@ class ProposalRoIEngine:
         sp = self._s_pool[j % self.n_pool_streams]
         sp.wait_event(self._ev_prop[j])
         with torch.cuda.stream(sp):
-            if pool_events:
+            if pool_events and pool_events[0] is not None:
                 pool_events[0].record(sp)
             self._pool(j, feature_maps)
-            if pool_events:
+            if pool_events and pool_events[1] is not None:
                 pool_events[1].record(sp)
             self._ev_pool[j].record(sp)
         self._pool_recorded[j] = True

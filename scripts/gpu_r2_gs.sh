@@ -1,0 +1,11 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/gs_bench_n1.json 2> gpurun_out/gs_bench_n1.err; echo "bench rc=$?"; tail -5 gpurun_out/gs_bench_n1.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/gs_bench_n1.json').read().strip().splitlines()[-1])
+r=d['roofline']
+print('kitti_b8 value %.0f ms/step %.4f kernel_ms %.4f (bracket %.4f eager span %.4f graph span %s) frac %.3f share %.3f clocks %s' % (d['value'], d['ms_per_step'], r['kernel_ms'], r['kernel_ms_bracketed'], r['kernel_ms_eager_span'], r['kernel_ms_graph_span'], r['frac'], r['share_of_step'], d['clocks']['sm_mhz']))
+for o in d['other_workloads']: print(o['workload'], {k:(round(v,4) if isinstance(v,float) else v) for k,v in o.items() if k in ('value','ms_per_step','kernel_ms','roofline_frac','step_latency_ms','clocks_sm_mhz','error')})
+PY
+echo "call GS done"
